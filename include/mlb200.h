@@ -1,0 +1,183 @@
+/* mlb200.h — the thin C-ABI between the ML++ host classes and the B200 (sm_100a) CUDA kernels.
+ *
+ * The reference (romanwerpachowski/ML) has no FFI for its clustering path: the boundary a user sees
+ * is the C++ class API (ML/Clustering.hpp:17-89, ML/EM.hpp:18-166, ML/KMeans.hpp:19-101) and the
+ * pybind module (cppyml/clustering.cpp:75-184).  Those are kept unchanged by the host layer under
+ * ml_b200/host/; this header is what that host layer calls, and what a replacement backend would
+ * have to export.  Each entry point names the reference loop it replaces.
+ *
+ * Conventions
+ *   - plain C, opaque handles, no exceptions, no torch/Eigen types;
+ *   - every function returns 0 on success or an MLB_E* code; mlb_last_error() gives the text of the
+ *     last failure on the calling thread;
+ *   - matrices are column-major exactly like Eigen::MatrixXd: data is D x N (a point per column,
+ *     D contiguous doubles per point), means/centroids are D x K, a covariance is D x D,
+ *     responsibilities are N x K (element (i,k) at i + k*N);
+ *   - a handle belongs to one host thread at a time;
+ *   - everything is FP64; labels are unsigned int as in the reference;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with MLB_ECUDA.
+ *
+ * Sharding.  The N points are cut into fixed "chunks" (a function of N only) and the chunks into 8
+ * contiguous virtual shards.  A context with G GPUs (G in {1,2,4,8}) gives 8/G consecutive virtual
+ * shards to each GPU.  Per-chunk partial statistics are summed in a fixed order inside a virtual
+ * shard, the 8 shard vectors are exchanged with ONE ncclAllGather per iteration and summed in the
+ * fixed tree ((0+1)+(2+3))+((4+5)+(6+7)) on every GPU, so results are bit-identical across ranks and
+ * across G.  
+ */
+#ifndef MLB200_H
+#define MLB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLB_OK 0
+#define MLB_EINVAL 1   /* bad argument (the reference throws std::invalid_argument / domain_error) */
+#define MLB_ECUDA 2    /* CUDA runtime / driver failure, or no device */
+#define MLB_ENCCL 3    /* NCCL failure */
+#define MLB_ENOMEM 4   /* device or host allocation failed */
+#define MLB_ESTATE 5   /* call sequence error (e.g. emit before any step) */
+
+#define MLB_VIRTUAL_SHARDS 8
+#define MLB_NCCL_UNIQUE_ID_BYTES 128
+
+typedef struct mlb_ctx mlb_ctx;   /* a set of GPUs: all local (one process), or one rank of a job */
+typedef struct mlb_data mlb_data; /* the point matrix, resident in HBM, sharded over the context */
+typedef struct mlb_em mlb_em;     /* Gaussian-mixture EM state (ml::EM, ML/EM.hpp:168-187) */
+typedef struct mlb_km mlb_km;     /* K-means state (ml::Clustering::KMeans, ML/KMeans.hpp:103-116) */
+
+/* ---------------------------------------------------------------- library */
+
+int mlb_version(void);                 /* 10000*major + 100*minor + patch */
+const char* mlb_last_error(void);      /* thread-local, never NULL */
+int mlb_device_count(int* count);      /* cudaGetDeviceCount */
+
+/* ---------------------------------------------------------------- context */
+
+/* One process driving n_devices local GPUs (n_devices in {1,2,4,8}); devices == NULL means
+ * 0..n_devices-1.  With n_devices > 1 the GPUs are joined by ncclCommInitAll. */
+int mlb_ctx_create(const int* devices, int n_devices, mlb_ctx** out);
+
+/* One process per GPU (torchrun style).  Rank 0 calls mlb_nccl_unique_id() and ships the 128
+ * bytes to the other ranks (any side channel: torch.distributed broadcast, a file, MPI);
+ * every rank then calls mlb_ctx_create_rank with the same id.  world in {1,2,4,8}. */
+int mlb_nccl_unique_id(void* out128);
+int mlb_ctx_create_rank(int device, int rank, int world, const void* nccl_unique_id128, mlb_ctx** out);
+
+int mlb_ctx_destroy(mlb_ctx* ctx);
+int mlb_ctx_world(const mlb_ctx* ctx, int* world, int* n_local, int* first_rank);
+
+/* Blocks until every local stream of the context is idle. */
+int mlb_ctx_synchronize(mlb_ctx* ctx);
+
+/* Elapsed device time helpers for benchmarks: CUDA events on the context's own streams
+ * (torch.cuda.Event cannot see them).  mlb_ctx_timer_stop returns the MAX over local GPUs, in ms. */
+int mlb_ctx_timer_start(mlb_ctx* ctx);
+int mlb_ctx_timer_stop(mlb_ctx* ctx, double* elapsed_ms);
+
+/* The half-open global point range [begin, end) that `rank` of `world` holds for a problem of
+ * n_total points.  A pure function (no context needed). */
+int mlb_shard_range(int64_t n_total, int world, int rank, int64_t* begin, int64_t* end);
+
+/* ---------------------------------------------------------------- data */
+
+/* Copies the host matrix (column-major D x n, outer stride ld >= d doubles) into HBM.
+ * Single-process contexts take the whole matrix (n == n_total) and scatter it over their GPUs.
+ * Rank contexts take the rank's own range of mlb_shard_range(n_total, world, rank).
+ * Replaces nothing in the reference (its data never leaves host memory); the reference's
+ * `fit(Eigen::Ref<const Eigen::MatrixXd> data)` argument is what is passed here (EM.cpp:91). */
+int mlb_data_upload(mlb_ctx* ctx, const double* x, int64_t n, int64_t n_total, int d, int64_t ld, mlb_data** out);
+
+/* Wraps points that already live in device memory of a 1-GPU context (no copy; the caller keeps
+ * ownership and must keep the buffer alive).  Point-contiguous, D doubles per point. */
+int mlb_data_wrap_device(mlb_ctx* ctx, const double* x_device, int64_t n, int d, mlb_data** out);
+
+/* Synthetic benchmark data generated in HBM: a K-component Gaussian mixture with
+ * means U[-spread, spread]^D, covariances A A^T / D + 0.5 I, Dirichlet-like weights; point i is a
+ * pure function of (seed, i) (Philox4x32-10 counter RNG), so every G sees identical data.
+ * true_means (D x k_true), if not NULL, receives the generating means. */
+int mlb_data_generate_gmm(mlb_ctx* ctx, int64_t n_total, int d, int k_true, uint64_t seed, double spread,
+                          double* true_means, mlb_data** out);
+
+/* Copies `count` points starting at GLOBAL index `begin` back to the host (column-major D x count).
+ * Rank contexts can only read their own range. */
+int mlb_data_download(mlb_data* data, int64_t begin, int64_t count, double* out);
+
+int mlb_data_shape(const mlb_data* data, int64_t* n_total, int64_t* n_local, int* d);
+int mlb_data_free(mlb_data* data);
+
+/* ---------------------------------------------------------------- Gaussian-mixture EM (ML/EM.cpp) */
+
+int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out);
+int mlb_em_destroy(mlb_em* em);
+
+/* EM::calculate_sample_covariance (EM.cpp:265-272): unbiased covariance of all points, D x D. */
+int mlb_em_sample_covariance(mlb_em* em, double* cov_out);
+
+/* Loads theta = (means D x K, covariances K blocks of D x D, mixing weights K) and runs
+ * EM::process_covariances (EM.cpp:274-287: Cholesky, inverse, sqrt|Sigma|) on the device. */
+int mlb_em_set_params(mlb_em* em, const double* means, const double* covariances, const double* weights);
+
+/* EM::maximisation_step (EM.cpp:221-263) from host responsibilities (N x K column-major; rank
+ * contexts pass their own rows, n_local x K with leading dimension n_local) — the
+ * `maximise_first` start (EM.cpp:120-125). */
+int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t ld);
+
+/* One iteration of the hot loop (EM.cpp:143-147): expectation_step with the current theta_t, then
+ * maximisation_step, fused on the device.  Returns the log-likelihood of theta_t (mean per point,
+ * EM.cpp:211).  theta_t is kept for mlb_em_emit. */
+int mlb_em_step(mlb_em* em, double* log_likelihood);
+
+/* Asynchronous variant for benchmarks: enqueues `steps` iterations without reading anything back.
+ * log_likelihoods (steps entries, may be NULL) is filled when the call returns (one sync at the end). */
+int mlb_em_run_steps(mlb_em* em, int steps, double* log_likelihoods);
+
+/* Current theta: means D x K, covariances K x (D x D), weights K.  Any pointer may be NULL. */
+int mlb_em_get_params(mlb_em* em, double* means, double* covariances, double* weights);
+
+/* process_covariances outputs for the current theta: inverse covariances K x (D x D) as computed by
+ * LLT::solve(Identity) and sqrt|Sigma_k| (EM.cpp:280-285); used by the host-side
+ * EM::assign_responsibilities (EM.cpp:176-188).  Any pointer may be NULL. */
+int mlb_em_get_precisions(mlb_em* em, double* inverse_covariances, double* sqrt_determinants);
+
+/* The E-step of the LAST mlb_em_step again, at the saved theta_t, writing what the reference
+ * leaves in responsibilities_ (EM.cpp:213-218; N x K column-major with leading dimension ld) and
+ * labels_ (EM.cpp:289-304; argmax, first maximum wins).  Either pointer may be NULL.
+ * Rank contexts receive their own rows. */
+int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_out);
+
+/* Which device path the last step used: 1 = fused DMMA E+M kernel, 2 = split E / M kernels. */
+int mlb_em_last_path(const mlb_em* em, int* path);
+/* Number of kernels the library launched on this object since creation (bench "gpu_launches"). */
+int mlb_em_launch_count(const mlb_em* em, int64_t* launches);
+
+/* ---------------------------------------------------------------- K-means (ML/KMeans.cpp) */
+
+int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out);
+int mlb_km_destroy(mlb_km* km);
+
+int mlb_km_set_centroids(mlb_km* km, const double* centroids /* D x K */);
+int mlb_km_get_centroids(mlb_km* km, double* centroids /* D x K */);
+
+/* KMeans::assignment_step (KMeans.cpp:167-178): swaps labels/old_labels, assigns every point to
+ * its nearest centroid (direct-difference squared distance, strict <, lowest k wins), returns the
+ * inertia and how many labels differ from the previous assignment (old_labels_ == labels_ of
+ * KMeans.cpp:85 is n_changed == 0).  Also accumulates the per-cluster counts and sums that
+ * mlb_km_update applies. */
+int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed);
+
+/* KMeans::update_step (KMeans.cpp:180-192): centroids <- per-cluster means of the last assignment
+ * (an empty cluster goes to the origin), old centroids kept; returns ||C - C_old||_F^2
+ * (KMeans.cpp:103). */
+int mlb_km_update(mlb_km* km, double* centroid_shift_sq);
+
+/* labels_ of the last assignment; rank contexts receive their own range. */
+int mlb_km_get_labels(mlb_km* km, unsigned int* labels);
+int mlb_km_launch_count(const mlb_km* km, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLB200_H */

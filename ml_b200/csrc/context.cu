@@ -1,0 +1,621 @@
+// Contexts (GPU sets), the resident point matrix, the synthetic generator and the deterministic
+// partial-statistics reduction + exchange shared by the EM and K-means paths.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+
+#include "internal.h"
+
+namespace mlb {
+
+static thread_local std::string g_last_error = "";
+
+void set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+Layout Layout::make(int64_t n_total)
+{
+    Layout lay;
+    lay.n_total = n_total;
+    // About 6 chunks per SM on each of 8 GPUs, in multiples of the 128-point tile, at most 4096
+    // points: small enough to balance 148 SMs, large enough that the per-chunk flush of partial
+    // statistics is noise.  Depends on n_total ONLY (never on the GPU count).
+    int64_t c = n_total / (8 * kSmCount * 6);
+    c = (c + 127) / 128 * 128;
+    c = std::max<int64_t>(128, std::min<int64_t>(4096, c));
+    lay.chunk = static_cast<int>(c);
+    lay.n_chunks = (n_total + c - 1) / c;
+    for (int v = 0; v <= kVirtualShards; ++v) lay.vshard_chunk[v] = lay.n_chunks * v / kVirtualShards;
+    return lay;
+}
+
+// ---------------------------------------------------------------- reduction of chunk partials
+
+struct VshardRanges {
+    int64_t lo[kVirtualShards];  // local chunk index ranges, one per local virtual shard
+    int64_t hi[kVirtualShards];
+};
+
+// out[v][e] = sum over the chunks of local virtual shard v of partials[c][e], in a fixed order:
+// four interleaved sequential accumulators combined as (a0+a1)+(a2+a3).
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, VshardRanges r, int s, double* __restrict__ out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (e >= s) return;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    const int64_t lo = r.lo[v], hi = r.hi[v];
+    int64_t c = lo;
+    for (; c + 3 < hi; c += 4) {
+        a0 += partials[(c + 0) * s + e];
+        a1 += partials[(c + 1) * s + e];
+        a2 += partials[(c + 2) * s + e];
+        a3 += partials[(c + 3) * s + e];
+    }
+    if (c < hi) a0 += partials[c * s + e];
+    if (c + 1 < hi) a1 += partials[(c + 1) * s + e];
+    if (c + 2 < hi) a2 += partials[(c + 2) * s + e];
+    out[static_cast<int64_t>(v) * s + e] = (a0 + a1) + (a2 + a3);
+}
+
+int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s)
+{
+    mlb_ctx* ctx = data->ctx;
+    const int vpg = ctx->vshards_per_gpu();
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        const DataShard& sh = data->shards[g];
+        VshardRanges r;
+        for (int j = 0; j < vpg; ++j) {
+            const int v = gpu.rank * vpg + j;
+            r.lo[j] = data->lay.vshard_chunk[v] - sh.chunk_begin;
+            r.hi[j] = data->lay.vshard_chunk[v + 1] - sh.chunk_begin;
+        }
+        dim3 grid((s + 255) / 256, vpg);
+        reduce_partials_kernel<<<grid, 256, 0, gpu.stream>>>(partials[g], r, s, vsum[g] + static_cast<int64_t>(gpu.rank) * vpg * s);
+        MLB_CUDA(cudaGetLastError());
+        return MLB_OK;
+    }));
+    if (ctx->world > 1) {
+        // ONE collective per iteration: every GPU contributes its 8/G shard vectors, in place.
+        MLB_NCCL(ncclGroupStart());
+        for (size_t g = 0; g < ctx->gpus.size(); ++g) {
+            Gpu& gpu = ctx->gpus[g];
+            const size_t count = static_cast<size_t>(vpg) * s;
+            MLB_NCCL(ncclAllGather(vsum[g] + static_cast<int64_t>(gpu.rank) * count, vsum[g], count, ncclDouble, gpu.comm, gpu.stream));
+        }
+        MLB_NCCL(ncclGroupEnd());
+    }
+    return MLB_OK;
+}
+
+// ---------------------------------------------------------------- column sums (data mean)
+
+// One block per chunk; thread t owns coordinate t % d of every (blockDim/d)-th point, then a fixed
+// shared-memory tree.  Deterministic.
+__global__ void column_sum_kernel(const double* __restrict__ x, int64_t n_local, int d, int chunk, double* __restrict__ partials)
+{
+    extern __shared__ double sm[];
+    const int64_t p0 = static_cast<int64_t>(blockIdx.x) * chunk;
+    const int64_t p1 = min(p0 + chunk, n_local);
+    const int lanes = blockDim.x / d;  // points handled concurrently
+    const int t = threadIdx.x;
+    const int c = t % d, lane = t / d;
+    double acc = 0;
+    if (lane < lanes) {
+        for (int64_t p = p0 + lane; p < p1; p += lanes) acc += x[p * d + c];
+    }
+    sm[t] = (lane < lanes) ? acc : 0.0;
+    __syncthreads();
+    if (t < d) {
+        double s = 0;
+        for (int l = 0; l < lanes; ++l) s += sm[l * d + t];
+        partials[static_cast<int64_t>(blockIdx.x) * d + t] = s;
+    }
+}
+
+static int compute_shift(mlb_data* data)
+{
+    mlb_ctx* ctx = data->ctx;
+    const int d = data->d;
+    std::vector<double*> partials(ctx->gpus.size(), nullptr), vsum(ctx->gpus.size(), nullptr);
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        DataShard& sh = data->shards[g];
+        MLB_CUDA(cudaMalloc(&partials[g], sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * d));
+        MLB_CUDA(cudaMalloc(&vsum[g], sizeof(double) * kVirtualShards * d));
+        MLB_CUDA(cudaMemsetAsync(vsum[g], 0, sizeof(double) * kVirtualShards * d, gpu.stream));
+        if (sh.n_chunks() > 0) {
+            const int threads = std::max(d, 256 / d * d);
+            column_sum_kernel<<<static_cast<unsigned>(sh.n_chunks()), threads, sizeof(double) * threads, gpu.stream>>>(
+                sh.x, sh.n(), d, data->lay.chunk, partials[g]);
+            MLB_CUDA(cudaGetLastError());
+        }
+        return MLB_OK;
+    }));
+    MLB_TRY(reduce_and_exchange(data, partials, vsum, d));
+    std::vector<double> host(static_cast<size_t>(kVirtualShards) * d);
+    MLB_CUDA(cudaSetDevice(ctx->gpus[0].device));
+    MLB_CUDA(cudaMemcpyAsync(host.data(), vsum[0], sizeof(double) * host.size(), cudaMemcpyDeviceToHost, ctx->gpus[0].stream));
+    MLB_TRY(mlb_ctx_synchronize(ctx));
+    data->shift.resize(d);
+    for (int c = 0; c < d; ++c) data->shift[c] = tree8(host.data() + c, d) / static_cast<double>(data->lay.n_total);
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        DataShard& sh = data->shards[g];
+        MLB_CUDA(cudaMalloc(&sh.shift, sizeof(double) * d));
+        MLB_CUDA(cudaMemcpyAsync(sh.shift, data->shift.data(), sizeof(double) * d, cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        MLB_CUDA(cudaFree(partials[g]));
+        MLB_CUDA(cudaFree(vsum[g]));
+        return MLB_OK;
+    }));
+    return MLB_OK;
+}
+
+// ---------------------------------------------------------------- synthetic GMM generator
+
+struct Philox {
+    // Philox4x32-10 (Salmon et al., SC'11): counter-based, so point i is a pure function of (seed, i).
+    static __host__ __device__ inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+    {
+        const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c[0];
+        const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c[2];
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
+        const uint32_t n1 = static_cast<uint32_t>(p1);
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
+        const uint32_t n3 = static_cast<uint32_t>(p0);
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    static __host__ __device__ inline void generate(uint64_t seed, uint64_t index, uint32_t stream, uint32_t (&out)[4])
+    {
+        uint32_t c[4] = {static_cast<uint32_t>(index), static_cast<uint32_t>(index >> 32), stream, 0u};
+        uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            round(c, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+    }
+    // uniform in (0, 1) from 53 random bits
+    static __host__ __device__ inline double u01(uint32_t hi, uint32_t lo)
+    {
+        const uint64_t bits = (static_cast<uint64_t>(hi) << 21) ^ (lo >> 11);
+        return (static_cast<double>(bits & ((1ull << 53) - 1)) + 0.5) * (1.0 / 9007199254740992.0);
+    }
+};
+
+constexpr int kMaxGenDim = 128;
+
+__global__ void generate_gmm_kernel(double* __restrict__ x, int64_t begin, int64_t n_local, int d, int k, uint64_t seed,
+                                    const double* __restrict__ means /*[k][d]*/, const double* __restrict__ chol /*[k][d][d] row-major lower*/,
+                                    const double* __restrict__ cum_weights /*[k]*/)
+{
+    const int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p >= n_local) return;
+    const uint64_t gi = static_cast<uint64_t>(begin + p);
+    uint32_t r[4];
+    Philox::generate(seed, gi, 0u, r);
+    const double u = Philox::u01(r[0], r[1]);
+    int comp = 0;
+    while (comp < k - 1 && u >= cum_weights[comp]) ++comp;
+    double z[kMaxGenDim];
+    for (int j = 0; j < d; j += 2) {
+        Philox::generate(seed, gi, 1u + static_cast<uint32_t>(j / 2), r);
+        const double u1 = Philox::u01(r[0], r[1]), u2 = Philox::u01(r[2], r[3]);
+        const double rad = sqrt(-2.0 * log(u1));
+        double s, c;
+        sincospi(2.0 * u2, &s, &c);
+        z[j] = rad * c;
+        if (j + 1 < d) z[j + 1] = rad * s;
+    }
+    const double* m = means + static_cast<int64_t>(comp) * d;
+    const double* l = chol + static_cast<int64_t>(comp) * d * d;
+    double* out = x + p * d;
+    for (int a = 0; a < d; ++a) {
+        double v = m[a];
+        for (int b = 0; b <= a; ++b) v += l[a * d + b] * z[b];
+        out[a] = v;
+    }
+}
+
+}  // namespace mlb
+
+using namespace mlb;
+
+// ======================================================================= C-ABI: library, context
+
+extern "C" {
+
+int mlb_version(void) { return 100; }
+
+const char* mlb_last_error(void) { return g_last_error.c_str(); }
+
+int mlb_device_count(int* count)
+{
+    MLB_REQUIRE(count, "mlb_device_count: null argument");
+    MLB_CUDA(cudaGetDeviceCount(count));
+    return MLB_OK;
+}
+
+static bool valid_world(int w) { return w == 1 || w == 2 || w == 4 || w == 8; }
+
+static int init_gpu(Gpu& gpu)
+{
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    MLB_CUDA(cudaStreamCreateWithFlags(&gpu.stream, cudaStreamNonBlocking));
+    MLB_CUDA(cudaEventCreate(&gpu.ev0));
+    MLB_CUDA(cudaEventCreate(&gpu.ev1));
+    return MLB_OK;
+}
+
+int mlb_ctx_create(const int* devices, int n_devices, mlb_ctx** out)
+{
+    MLB_REQUIRE(out, "mlb_ctx_create: null output");
+    MLB_REQUIRE(valid_world(n_devices), "mlb_ctx_create: n_devices must be 1, 2, 4 or 8 (got %d)", n_devices);
+    int available = 0;
+    MLB_CUDA(cudaGetDeviceCount(&available));
+    if (available < 1) {
+        set_error("mlb_ctx_create: no CUDA device (this library has no CPU fallback)");
+        return MLB_ECUDA;
+    }
+    auto* ctx = new mlb_ctx;
+    ctx->world = n_devices;
+    ctx->rank_mode = false;
+    ctx->gpus.resize(n_devices);
+    std::vector<int> devs(n_devices);
+    for (int g = 0; g < n_devices; ++g) {
+        devs[g] = devices ? devices[g] : g;
+        if (devs[g] < 0 || devs[g] >= available) {
+            set_error("mlb_ctx_create: device %d not available (%d visible)", devs[g], available);
+            delete ctx;
+            return MLB_EINVAL;
+        }
+        ctx->gpus[g].device = devs[g];
+        ctx->gpus[g].rank = g;
+        int rc = init_gpu(ctx->gpus[g]);
+        if (rc != MLB_OK) { delete ctx; return rc; }
+    }
+    if (n_devices > 1) {
+        std::vector<ncclComm_t> comms(n_devices);
+        ncclResult_t r = ncclCommInitAll(comms.data(), n_devices, devs.data());
+        if (r != ncclSuccess) {
+            set_error("ncclCommInitAll failed: %s", ncclGetErrorString(r));
+            delete ctx;
+            return MLB_ENCCL;
+        }
+        for (int g = 0; g < n_devices; ++g) ctx->gpus[g].comm = comms[g];
+    }
+    *out = ctx;
+    return MLB_OK;
+}
+
+int mlb_nccl_unique_id(void* out128)
+{
+    MLB_REQUIRE(out128, "mlb_nccl_unique_id: null output");
+    static_assert(sizeof(ncclUniqueId) == MLB_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    MLB_NCCL(ncclGetUniqueId(&id));
+    std::memcpy(out128, &id, sizeof(id));
+    return MLB_OK;
+}
+
+int mlb_ctx_create_rank(int device, int rank, int world, const void* nccl_unique_id128, mlb_ctx** out)
+{
+    MLB_REQUIRE(out, "mlb_ctx_create_rank: null output");
+    MLB_REQUIRE(valid_world(world), "mlb_ctx_create_rank: world must be 1, 2, 4 or 8 (got %d)", world);
+    MLB_REQUIRE(rank >= 0 && rank < world, "mlb_ctx_create_rank: bad rank %d of %d", rank, world);
+    MLB_REQUIRE(world == 1 || nccl_unique_id128, "mlb_ctx_create_rank: NCCL unique id required for world > 1");
+    int available = 0;
+    MLB_CUDA(cudaGetDeviceCount(&available));
+    MLB_REQUIRE(device >= 0 && device < available, "mlb_ctx_create_rank: device %d not available (%d visible)", device, available);
+    auto* ctx = new mlb_ctx;
+    ctx->world = world;
+    ctx->rank_mode = true;
+    ctx->gpus.resize(1);
+    ctx->gpus[0].device = device;
+    ctx->gpus[0].rank = rank;
+    int rc = init_gpu(ctx->gpus[0]);
+    if (rc != MLB_OK) { delete ctx; return rc; }
+    if (world > 1) {
+        ncclUniqueId id;
+        std::memcpy(&id, nccl_unique_id128, sizeof(id));
+        ncclResult_t r = ncclCommInitRank(&ctx->gpus[0].comm, world, id, rank);
+        if (r != ncclSuccess) {
+            set_error("ncclCommInitRank failed: %s", ncclGetErrorString(r));
+            delete ctx;
+            return MLB_ENCCL;
+        }
+    }
+    *out = ctx;
+    return MLB_OK;
+}
+
+int mlb_ctx_destroy(mlb_ctx* ctx)
+{
+    if (!ctx) return MLB_OK;
+    for (Gpu& gpu : ctx->gpus) {
+        cudaSetDevice(gpu.device);
+        if (gpu.stream) cudaStreamSynchronize(gpu.stream);
+        if (gpu.comm) ncclCommDestroy(gpu.comm);
+        if (gpu.ev0) cudaEventDestroy(gpu.ev0);
+        if (gpu.ev1) cudaEventDestroy(gpu.ev1);
+        if (gpu.stream) cudaStreamDestroy(gpu.stream);
+    }
+    delete ctx;
+    return MLB_OK;
+}
+
+int mlb_ctx_world(const mlb_ctx* ctx, int* world, int* n_local, int* first_rank)
+{
+    MLB_REQUIRE(ctx, "mlb_ctx_world: null context");
+    if (world) *world = ctx->world;
+    if (n_local) *n_local = static_cast<int>(ctx->gpus.size());
+    if (first_rank) *first_rank = ctx->gpus[0].rank;
+    return MLB_OK;
+}
+
+int mlb_ctx_synchronize(mlb_ctx* ctx)
+{
+    MLB_REQUIRE(ctx, "mlb_ctx_synchronize: null context");
+    return for_each_gpu(ctx, [&](int, Gpu& gpu) -> int {
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    });
+}
+
+int mlb_ctx_timer_start(mlb_ctx* ctx)
+{
+    MLB_REQUIRE(ctx, "mlb_ctx_timer_start: null context");
+    return for_each_gpu(ctx, [&](int, Gpu& gpu) -> int {
+        MLB_CUDA(cudaEventRecord(gpu.ev0, gpu.stream));
+        return MLB_OK;
+    });
+}
+
+int mlb_ctx_timer_stop(mlb_ctx* ctx, double* elapsed_ms)
+{
+    MLB_REQUIRE(ctx && elapsed_ms, "mlb_ctx_timer_stop: null argument");
+    MLB_TRY(for_each_gpu(ctx, [&](int, Gpu& gpu) -> int {
+        MLB_CUDA(cudaEventRecord(gpu.ev1, gpu.stream));
+        return MLB_OK;
+    }));
+    double worst = 0;
+    MLB_TRY(for_each_gpu(ctx, [&](int, Gpu& gpu) -> int {
+        MLB_CUDA(cudaEventSynchronize(gpu.ev1));
+        float ms = 0;
+        MLB_CUDA(cudaEventElapsedTime(&ms, gpu.ev0, gpu.ev1));
+        worst = std::max(worst, static_cast<double>(ms));
+        return MLB_OK;
+    }));
+    *elapsed_ms = worst;
+    return MLB_OK;
+}
+
+int mlb_shard_range(int64_t n_total, int world, int rank, int64_t* begin, int64_t* end)
+{
+    MLB_REQUIRE(n_total >= 0 && valid_world(world) && rank >= 0 && rank < world, "mlb_shard_range: bad arguments");
+    const Layout lay = Layout::make(n_total);
+    const int vpg = kVirtualShards / world;
+    if (begin) *begin = lay.point_begin(rank * vpg);
+    if (end) *end = lay.point_begin((rank + 1) * vpg);
+    return MLB_OK;
+}
+
+// ======================================================================= C-ABI: data
+
+static int make_shards(mlb_ctx* ctx, int64_t n_total, int d, mlb_data** out)
+{
+    auto* data = new mlb_data;
+    data->ctx = ctx;
+    data->d = d;
+    data->lay = Layout::make(n_total);
+    const int vpg = ctx->vshards_per_gpu();
+    data->shards.resize(ctx->gpus.size());
+    for (size_t g = 0; g < ctx->gpus.size(); ++g) {
+        const int rank = ctx->gpus[g].rank;
+        DataShard& sh = data->shards[g];
+        sh.chunk_begin = data->lay.vshard_chunk[rank * vpg];
+        sh.chunk_end = data->lay.vshard_chunk[(rank + 1) * vpg];
+        sh.begin = data->lay.point_begin(rank * vpg);
+        sh.end = data->lay.point_begin((rank + 1) * vpg);
+    }
+    *out = data;
+    return MLB_OK;
+}
+
+int mlb_data_free(mlb_data* data)
+{
+    if (!data) return MLB_OK;
+    for (size_t g = 0; g < data->shards.size(); ++g) {
+        cudaSetDevice(data->ctx->gpus[g].device);
+        cudaStreamSynchronize(data->ctx->gpus[g].stream);
+        if (data->shards[g].owned && data->shards[g].x) cudaFree(data->shards[g].x);
+        if (data->shards[g].shift) cudaFree(data->shards[g].shift);
+    }
+    delete data;
+    return MLB_OK;
+}
+
+int mlb_data_upload(mlb_ctx* ctx, const double* x, int64_t n, int64_t n_total, int d, int64_t ld, mlb_data** out)
+{
+    MLB_REQUIRE(ctx && x && out, "mlb_data_upload: null argument");
+    MLB_REQUIRE(d >= 1, "mlb_data_upload: at least one dimension required");
+    MLB_REQUIRE(ld >= d, "mlb_data_upload: outer stride %lld smaller than d=%d", static_cast<long long>(ld), d);
+    MLB_REQUIRE(n_total >= 1 && n_total < (1ll << 32), "mlb_data_upload: n_total out of range");
+    mlb_data* data = nullptr;
+    MLB_TRY(make_shards(ctx, n_total, d, &data));
+    const int64_t host_begin = ctx->rank_mode ? data->shards[0].begin : 0;
+    const int64_t expect = ctx->rank_mode ? data->shards[0].n() : n_total;
+    if (n != expect) {
+        set_error("mlb_data_upload: got %lld points, expected %lld for this context", static_cast<long long>(n), static_cast<long long>(expect));
+        mlb_data_free(data);
+        return MLB_EINVAL;
+    }
+    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        DataShard& sh = data->shards[g];
+        MLB_CUDA(cudaMalloc(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d));
+        if (sh.n() > 0) {
+            const double* src = x + (sh.begin - host_begin) * ld;
+            if (ld == d) {
+                MLB_CUDA(cudaMemcpyAsync(sh.x, src, sizeof(double) * sh.n() * d, cudaMemcpyHostToDevice, gpu.stream));
+            } else {
+                MLB_CUDA(cudaMemcpy2DAsync(sh.x, sizeof(double) * d, src, sizeof(double) * ld, sizeof(double) * d, sh.n(),
+                                           cudaMemcpyHostToDevice, gpu.stream));
+            }
+        }
+        return MLB_OK;
+    });
+    if (rc == MLB_OK) rc = compute_shift(data);
+    if (rc != MLB_OK) {
+        mlb_data_free(data);
+        return rc;
+    }
+    *out = data;
+    return MLB_OK;
+}
+
+int mlb_data_wrap_device(mlb_ctx* ctx, const double* x_device, int64_t n, int d, mlb_data** out)
+{
+    MLB_REQUIRE(ctx && x_device && out, "mlb_data_wrap_device: null argument");
+    MLB_REQUIRE(ctx->world == 1, "mlb_data_wrap_device: 1-GPU contexts only");
+    MLB_REQUIRE(d >= 1 && n >= 1 && n < (1ll << 32), "mlb_data_wrap_device: bad shape");
+    mlb_data* data = nullptr;
+    MLB_TRY(make_shards(ctx, n, d, &data));
+    data->shards[0].x = const_cast<double*>(x_device);
+    data->shards[0].owned = false;
+    int rc = compute_shift(data);
+    if (rc != MLB_OK) {
+        mlb_data_free(data);
+        return rc;
+    }
+    *out = data;
+    return MLB_OK;
+}
+
+int mlb_data_generate_gmm(mlb_ctx* ctx, int64_t n_total, int d, int k_true, uint64_t seed, double spread,
+                          double* true_means, mlb_data** out)
+{
+    MLB_REQUIRE(ctx && out, "mlb_data_generate_gmm: null argument");
+    MLB_REQUIRE(d >= 1 && d <= kMaxGenDim && k_true >= 1 && n_total >= 1 && n_total < (1ll << 32), "mlb_data_generate_gmm: bad shape");
+    // Mixture parameters: a pure function of (seed, d, k_true), drawn on the host.
+    std::mt19937_64 rng(seed * 0x9E3779B97F4A7C15ull + 12345u);
+    auto unif = [&]() { return (static_cast<double>(rng() >> 11) + 0.5) * (1.0 / 9007199254740992.0); };
+    auto normal = [&]() {
+        const double u1 = unif(), u2 = unif();
+        return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+    };
+    std::vector<double> means(static_cast<size_t>(k_true) * d), chol(static_cast<size_t>(k_true) * d * d, 0.0), cum(k_true);
+    for (double& m : means) m = spread * (2.0 * unif() - 1.0);
+    std::vector<double> a(static_cast<size_t>(d) * d), cov(static_cast<size_t>(d) * d);
+    for (int c = 0; c < k_true; ++c) {
+        for (double& v : a) v = normal();
+        for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+                double s = 0;
+                for (int l = 0; l < d; ++l) s += a[i * d + l] * a[j * d + l];
+                cov[i * d + j] = s / d + (i == j ? 0.5 : 0.0);
+            }
+        double* l = chol.data() + static_cast<size_t>(c) * d * d;
+        for (int j = 0; j < d; ++j) {
+            double s = cov[j * d + j];
+            for (int t = 0; t < j; ++t) s -= l[j * d + t] * l[j * d + t];
+            l[j * d + j] = std::sqrt(s);
+            for (int i = j + 1; i < d; ++i) {
+                double v = cov[i * d + j];
+                for (int t = 0; t < j; ++t) v -= l[i * d + t] * l[j * d + t];
+                l[i * d + j] = v / l[j * d + j];
+            }
+        }
+    }
+    {
+        // Dirichlet(5)-like weights: normalised sums of 5 unit exponentials (= Gamma(5, 1)).
+        double total = 0;
+        for (int c = 0; c < k_true; ++c) {
+            double g = 0;
+            for (int j = 0; j < 5; ++j) g -= std::log(unif());
+            cum[c] = g;
+            total += g;
+        }
+        double run = 0;
+        for (int c = 0; c < k_true; ++c) {
+            run += cum[c] / total;
+            cum[c] = run;
+        }
+        cum[k_true - 1] = 1.0;
+    }
+    if (true_means) std::memcpy(true_means, means.data(), sizeof(double) * means.size());
+    mlb_data* data = nullptr;
+    MLB_TRY(make_shards(ctx, n_total, d, &data));
+    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        DataShard& sh = data->shards[g];
+        MLB_CUDA(cudaMalloc(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d));
+        double *dm = nullptr, *dl = nullptr, *dw = nullptr;
+        MLB_CUDA(cudaMalloc(&dm, sizeof(double) * means.size()));
+        MLB_CUDA(cudaMalloc(&dl, sizeof(double) * chol.size()));
+        MLB_CUDA(cudaMalloc(&dw, sizeof(double) * cum.size()));
+        MLB_CUDA(cudaMemcpyAsync(dm, means.data(), sizeof(double) * means.size(), cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(dl, chol.data(), sizeof(double) * chol.size(), cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(dw, cum.data(), sizeof(double) * cum.size(), cudaMemcpyHostToDevice, gpu.stream));
+        if (sh.n() > 0) {
+            const unsigned blocks = static_cast<unsigned>((sh.n() + 127) / 128);
+            generate_gmm_kernel<<<blocks, 128, 0, gpu.stream>>>(sh.x, sh.begin, sh.n(), d, k_true, seed, dm, dl, dw);
+            MLB_CUDA(cudaGetLastError());
+        }
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        MLB_CUDA(cudaFree(dm));
+        MLB_CUDA(cudaFree(dl));
+        MLB_CUDA(cudaFree(dw));
+        return MLB_OK;
+    });
+    if (rc == MLB_OK) rc = compute_shift(data);
+    if (rc != MLB_OK) {
+        mlb_data_free(data);
+        return rc;
+    }
+    *out = data;
+    return MLB_OK;
+}
+
+int mlb_data_download(mlb_data* data, int64_t begin, int64_t count, double* out)
+{
+    MLB_REQUIRE(data && out, "mlb_data_download: null argument");
+    MLB_REQUIRE(begin >= 0 && count >= 0 && begin + count <= data->lay.n_total, "mlb_data_download: range out of bounds");
+    const int d = data->d;
+    int64_t covered = 0;
+    MLB_TRY(for_each_gpu(data->ctx, [&](int g, Gpu& gpu) -> int {
+        const DataShard& sh = data->shards[g];
+        const int64_t lo = std::max(begin, sh.begin), hi = std::min(begin + count, sh.end);
+        if (lo < hi) {
+            MLB_CUDA(cudaMemcpyAsync(out + (lo - begin) * d, sh.x + (lo - sh.begin) * d, sizeof(double) * (hi - lo) * d,
+                                     cudaMemcpyDeviceToHost, gpu.stream));
+            MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+            covered += hi - lo;
+        }
+        return MLB_OK;
+    }));
+    MLB_REQUIRE(covered == count, "mlb_data_download: range is not held by this context");
+    return MLB_OK;
+}
+
+int mlb_data_shape(const mlb_data* data, int64_t* n_total, int64_t* n_local, int* d)
+{
+    MLB_REQUIRE(data, "mlb_data_shape: null data");
+    if (n_total) *n_total = data->lay.n_total;
+    if (n_local) {
+        int64_t n = 0;
+        for (const DataShard& sh : data->shards) n += sh.n();
+        *n_local = n;
+    }
+    if (d) *d = data->d;
+    return MLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// Internal structures shared by the translation units of libmlb200.so.  Not part of the C-ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/mlb200.h"
+
+namespace mlb {
+
+void set_error(const char* fmt, ...);
+
+#define MLB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t mlb_e_ = (expr);                                                            \
+        if (mlb_e_ != cudaSuccess) {                                                            \
+            ::mlb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(mlb_e_)); \
+            return (mlb_e_ == cudaErrorMemoryAllocation) ? MLB_ENOMEM : MLB_ECUDA;              \
+        }                                                                                       \
+    } while (0)
+
+#define MLB_NCCL(expr)                                                                          \
+    do {                                                                                        \
+        ncclResult_t mlb_n_ = (expr);                                                           \
+        if (mlb_n_ != ncclSuccess) {                                                            \
+            ::mlb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, ncclGetErrorString(mlb_n_)); \
+            return MLB_ENCCL;                                                                   \
+        }                                                                                       \
+    } while (0)
+
+#define MLB_TRY(expr)                   \
+    do {                                \
+        int mlb_rc_ = (expr);           \
+        if (mlb_rc_ != MLB_OK) return mlb_rc_; \
+    } while (0)
+
+#define MLB_REQUIRE(cond, ...)            \
+    do {                                  \
+        if (!(cond)) {                    \
+            ::mlb::set_error(__VA_ARGS__); \
+            return MLB_EINVAL;            \
+        }                                 \
+    } while (0)
+
+constexpr int kVirtualShards = MLB_VIRTUAL_SHARDS;
+constexpr int kSmCount = 148;  // B200
+
+// How the N points are cut up.  A pure function of n_total, so that every GPU count sees the same
+// chunks and therefore the same summation tree (bitwise G-invariance).
+struct Layout {
+    int64_t n_total = 0;
+    int chunk = 0;                            // points per chunk (multiple of 128)
+    int64_t n_chunks = 0;                     // ceil(n_total / chunk)
+    int64_t vshard_chunk[kVirtualShards + 1]; // chunk boundaries of the virtual shards
+
+    static Layout make(int64_t n_total);
+    int64_t point_begin(int vshard) const { return std::min<int64_t>(vshard_chunk[vshard] * chunk, n_total); }
+};
+
+// One local GPU of a context.
+struct Gpu {
+    int device = 0;
+    int rank = 0;  // global rank of this GPU in [0, world)
+    cudaStream_t stream = nullptr;
+    ncclComm_t comm = nullptr;  // null when world == 1
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+}  // namespace mlb
+
+struct mlb_ctx {
+    int world = 1;          // total GPUs in the job
+    bool rank_mode = false; // one process per GPU
+    std::vector<mlb::Gpu> gpus;  // the local ones, consecutive ranks
+    int vshards_per_gpu() const { return mlb::kVirtualShards / world; }
+};
+
+namespace mlb {
+
+// The slice of the data one local GPU holds.
+struct DataShard {
+    double* x = nullptr;       // point-contiguous, d doubles per point
+    bool owned = true;
+    int64_t begin = 0, end = 0;           // global point range
+    int64_t chunk_begin = 0, chunk_end = 0;  // global chunk range
+    double* shift = nullptr;   // d doubles: the global data mean (device copy)
+    int64_t n() const { return end - begin; }
+    int64_t n_chunks() const { return chunk_end - chunk_begin; }
+};
+
+}  // namespace mlb
+
+struct mlb_data {
+    mlb_ctx* ctx = nullptr;
+    mlb::Layout lay;
+    int d = 0;
+    std::vector<mlb::DataShard> shards;  // one per local GPU
+    std::vector<double> shift;           // host copy of the global data mean
+};
+
+namespace mlb {
+
+// Runs body(g, gpu) for every local GPU with that GPU's device made current.
+template <class F>
+int for_each_gpu(mlb_ctx* ctx, F&& body)
+{
+    for (size_t g = 0; g < ctx->gpus.size(); ++g) {
+        MLB_CUDA(cudaSetDevice(ctx->gpus[g].device));
+        MLB_TRY(body(static_cast<int>(g), ctx->gpus[g]));
+    }
+    return MLB_OK;
+}
+
+// Reduces per-chunk partial vectors to the 8 virtual-shard vectors and exchanges them.
+//   partials[g]: device, [local chunks of GPU g][s]
+//   vsum[g]:     device, [8][s]; on return every GPU holds all 8 shard vectors.
+// Fixed summation order => deterministic and independent of the GPU count.
+int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s);
+
+// Host-side fixed tree over the 8 virtual-shard vectors: ((0+1)+(2+3))+((4+5)+(6+7)).
+inline double tree8(const double* v, int64_t stride)
+{
+    return ((v[0] + v[stride]) + (v[2 * stride] + v[3 * stride])) + ((v[4 * stride] + v[5 * stride]) + (v[6 * stride] + v[7 * stride]));
+}
+
+}  // namespace mlb
