@@ -1,0 +1,361 @@
+"""ctypes binding of the C-ABI in include/mlb200.h (libmlb200.so).
+
+This is the Python face of the same boundary the C++ host classes (ml_b200/host) call.  It never
+imports the CPU oracle and has no fallback: loading fails loudly if the CUDA library is missing,
+and every compute entry point fails with MLB_ECUDA when there is no device.
+
+Matrices follow the reference's convention: column-major D x N data, which is the memory of a
+C-contiguous numpy array of shape (N, D); means are (D, K) in the reference and cross this module
+as C-contiguous (K, D) arrays (the same memory).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmlb200.so")
+
+MLB_OK, MLB_EINVAL, MLB_ECUDA, MLB_ENCCL, MLB_ENOMEM, MLB_ESTATE = range(6)
+
+_c_dp = ctypes.POINTER(ctypes.c_double)
+_c_up = ctypes.POINTER(ctypes.c_uint)
+_c_i64p = ctypes.POINTER(ctypes.c_int64)
+_c_ip = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+
+# name -> (restype, argtypes).  tests/test_cabi_symbols.py checks this table against the header.
+SIGNATURES = {
+    "mlb_version": (ctypes.c_int, []),
+    "mlb_last_error": (ctypes.c_char_p, []),
+    "mlb_device_count": (ctypes.c_int, [_c_ip]),
+    "mlb_ctx_create": (ctypes.c_int, [_c_ip, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "mlb_nccl_unique_id": (ctypes.c_int, [_vp]),
+    "mlb_ctx_create_rank": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(_vp)]),
+    "mlb_ctx_destroy": (ctypes.c_int, [_vp]),
+    "mlb_ctx_world": (ctypes.c_int, [_vp, _c_ip, _c_ip, _c_ip]),
+    "mlb_ctx_synchronize": (ctypes.c_int, [_vp]),
+    "mlb_ctx_timer_start": (ctypes.c_int, [_vp]),
+    "mlb_ctx_timer_stop": (ctypes.c_int, [_vp, _c_dp]),
+    "mlb_shard_range": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _c_i64p, _c_i64p]),
+    "mlb_data_upload": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.POINTER(_vp)]),
+    "mlb_data_wrap_device": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "mlb_data_generate_gmm": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_double, _vp,
+                                             ctypes.POINTER(_vp)]),
+    "mlb_data_download": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),
+    "mlb_data_shape": (ctypes.c_int, [_vp, _c_i64p, _c_i64p, _c_ip]),
+    "mlb_data_free": (ctypes.c_int, [_vp]),
+    "mlb_em_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "mlb_em_destroy": (ctypes.c_int, [_vp]),
+    "mlb_em_sample_covariance": (ctypes.c_int, [_vp, _vp]),
+    "mlb_em_set_params": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "mlb_em_mstep_from_responsibilities": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
+    "mlb_em_step": (ctypes.c_int, [_vp, _c_dp]),
+    "mlb_em_run_steps": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "mlb_em_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "mlb_em_get_precisions": (ctypes.c_int, [_vp, _vp, _vp]),
+    "mlb_em_emit": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
+    "mlb_em_last_path": (ctypes.c_int, [_vp, _c_ip]),
+    "mlb_em_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
+    "mlb_km_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "mlb_km_destroy": (ctypes.c_int, [_vp]),
+    "mlb_km_set_centroids": (ctypes.c_int, [_vp, _vp]),
+    "mlb_km_get_centroids": (ctypes.c_int, [_vp, _vp]),
+    "mlb_km_assign": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
+    "mlb_km_update": (ctypes.c_int, [_vp, _c_dp]),
+    "mlb_km_get_labels": (ctypes.c_int, [_vp, _vp]),
+    "mlb_km_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
+}
+
+_lib = None
+
+
+class MlbError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"libmlb200 error {code}: {text}")
+        self.code = code
+
+
+def lib():
+    """Loads libmlb200.so (built by __graft_entry__.build() / `make -C ml_b200/csrc`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `make -C ml_b200/csrc` (there is no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != MLB_OK:
+        raise MlbError(rc, lib().mlb_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def device_count():
+    n = ctypes.c_int()
+    check(lib().mlb_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def shard_range(n_total, world, rank):
+    b, e = ctypes.c_int64(), ctypes.c_int64()
+    check(lib().mlb_shard_range(n_total, world, rank, ctypes.byref(b), ctypes.byref(e)))
+    return b.value, e.value
+
+
+def nccl_unique_id():
+    buf = (ctypes.c_ubyte * 128)()
+    check(lib().mlb_nccl_unique_id(ctypes.cast(buf, _vp)))
+    return bytes(buf)
+
+
+class Context:
+    """A set of GPUs: `Context(n_devices=G)` drives G local GPUs from this process;
+    `Context.for_rank(device, rank, world, unique_id)` is one rank of a torchrun-style job."""
+
+    def __init__(self, n_devices=1, devices=None, _handle=None):
+        self._h = _vp()
+        if _handle is not None:
+            self._h = _handle
+            return
+        arr = None
+        if devices is not None:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            n_devices = len(devices)
+        check(lib().mlb_ctx_create(arr, n_devices, ctypes.byref(self._h)))
+
+    @classmethod
+    def for_rank(cls, device, rank, world, unique_id):
+        h = _vp()
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        check(lib().mlb_ctx_create_rank(device, rank, world, ctypes.cast(buf, _vp) if buf is not None else None, ctypes.byref(h)))
+        return cls(_handle=h)
+
+    @property
+    def world(self):
+        w, n, f = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(lib().mlb_ctx_world(self._h, ctypes.byref(w), ctypes.byref(n), ctypes.byref(f)))
+        return w.value
+
+    def synchronize(self):
+        check(lib().mlb_ctx_synchronize(self._h))
+
+    def timer_start(self):
+        check(lib().mlb_ctx_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_double()
+        check(lib().mlb_ctx_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if self._h:
+            lib().mlb_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Data:
+    """The point matrix resident in HBM."""
+
+    def __init__(self, ctx, handle, keep=None):
+        self.ctx = ctx
+        self._h = handle
+        self._keep = keep
+
+    @classmethod
+    def upload(cls, ctx, points, n_total=None):
+        """`points`: C-contiguous float64 (n, D), i.e. column-major D x n.  Rank contexts pass their own rows."""
+        if points.dtype != np.float64 or points.ndim != 2 or not points.flags.c_contiguous:
+            raise TypeError("points must be a C-contiguous float64 array of shape (N, D)")
+        n, d = points.shape
+        h = _vp()
+        check(lib().mlb_data_upload(ctx._h, _ptr(points), n, n if n_total is None else n_total, d, d, ctypes.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def wrap_device(cls, ctx, device_ptr, n, d, keep=None):
+        h = _vp()
+        check(lib().mlb_data_wrap_device(ctx._h, _vp(device_ptr), n, d, ctypes.byref(h)))
+        return cls(ctx, h, keep)
+
+    @classmethod
+    def generate_gmm(cls, ctx, n_total, d, k_true, seed=1, spread=10.0):
+        h = _vp()
+        true_means = np.zeros((k_true, d))
+        check(lib().mlb_data_generate_gmm(ctx._h, n_total, d, k_true, seed, spread, _ptr(true_means), ctypes.byref(h)))
+        out = cls(ctx, h)
+        out.true_means = true_means
+        return out
+
+    @property
+    def shape(self):
+        n, nl, d = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+        check(lib().mlb_data_shape(self._h, ctypes.byref(n), ctypes.byref(nl), ctypes.byref(d)))
+        return n.value, nl.value, d.value
+
+    def download(self, begin, count):
+        _, _, d = self.shape
+        out = np.empty((count, d))
+        check(lib().mlb_data_download(self._h, begin, count, _ptr(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().mlb_data_free(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Em:
+    """Device state of one ml::EM fit (ML/EM.hpp:168-187)."""
+
+    def __init__(self, data, k):
+        self.data = data
+        self.k = k
+        self.n_total, self.n_local, self.d = data.shape
+        self._h = _vp()
+        check(lib().mlb_em_create(data.ctx._h, data._h, k, ctypes.byref(self._h)))
+
+    def sample_covariance(self):
+        cov = np.empty((self.d, self.d))
+        check(lib().mlb_em_sample_covariance(self._h, _ptr(cov)))
+        return cov
+
+    def set_params(self, means_dk, covariances, weights):
+        """means_dk: (D, K) like ml::EM::means(); covariances: (K, D, D); weights: (K,)."""
+        means = np.ascontiguousarray(np.asarray(means_dk, dtype=np.float64).T)
+        covs = np.ascontiguousarray(np.asarray(covariances, dtype=np.float64).transpose(0, 2, 1))
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert means.shape == (self.k, self.d) and covs.shape == (self.k, self.d, self.d) and w.shape == (self.k,)
+        check(lib().mlb_em_set_params(self._h, _ptr(means), _ptr(covs), _ptr(w)))
+
+    def mstep_from_responsibilities(self, resp_nk):
+        """resp_nk: (n, K) responsibilities as ml::EM::responsibilities() (column-major N x K)."""
+        r = np.asfortranarray(resp_nk, dtype=np.float64)
+        check(lib().mlb_em_mstep_from_responsibilities(self._h, _ptr(r), r.shape[0]))
+
+    def step(self):
+        ll = ctypes.c_double()
+        check(lib().mlb_em_step(self._h, ctypes.byref(ll)))
+        return ll.value
+
+    def run_steps(self, steps, want_ll=True):
+        lls = np.empty(steps) if want_ll else None
+        check(lib().mlb_em_run_steps(self._h, steps, _ptr(lls)))
+        return lls
+
+    def get_params(self):
+        means = np.empty((self.k, self.d))
+        covs = np.empty((self.k, self.d, self.d))
+        w = np.empty(self.k)
+        check(lib().mlb_em_get_params(self._h, _ptr(means), _ptr(covs), _ptr(w)))
+        return means.T.copy(), covs.transpose(0, 2, 1).copy(), w
+
+    def get_precisions(self):
+        inv = np.empty((self.k, self.d, self.d))
+        sd = np.empty(self.k)
+        check(lib().mlb_em_get_precisions(self._h, _ptr(inv), _ptr(sd)))
+        return inv.transpose(0, 2, 1).copy(), sd
+
+    def emit(self, want_responsibilities=True, want_labels=True, rows=None):
+        n = self.n_local if rows is None else rows
+        resp = np.empty((n, self.k), order="F") if want_responsibilities else None
+        labels = np.empty(n, dtype=np.uint32) if want_labels else None
+        check(lib().mlb_em_emit(self._h, _ptr(resp), n, _ptr(labels)))
+        return resp, labels
+
+    @property
+    def last_path(self):
+        p = ctypes.c_int()
+        check(lib().mlb_em_last_path(self._h, ctypes.byref(p)))
+        return p.value
+
+    @property
+    def launch_count(self):
+        c = ctypes.c_int64()
+        check(lib().mlb_em_launch_count(self._h, ctypes.byref(c)))
+        return c.value
+
+    def close(self):
+        if self._h:
+            lib().mlb_em_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Km:
+    """Device state of one ml::Clustering::KMeans fit (ML/KMeans.hpp:103-116)."""
+
+    def __init__(self, data, k):
+        self.data = data
+        self.k = k
+        self.n_total, self.n_local, self.d = data.shape
+        self._h = _vp()
+        check(lib().mlb_km_create(data.ctx._h, data._h, k, ctypes.byref(self._h)))
+
+    def set_centroids(self, centroids_dk):
+        c = np.ascontiguousarray(np.asarray(centroids_dk, dtype=np.float64).T)
+        assert c.shape == (self.k, self.d)
+        check(lib().mlb_km_set_centroids(self._h, _ptr(c)))
+
+    def get_centroids(self):
+        c = np.empty((self.k, self.d))
+        check(lib().mlb_km_get_centroids(self._h, _ptr(c)))
+        return c.T.copy()
+
+    def assign(self):
+        inertia, changed = ctypes.c_double(), ctypes.c_int64()
+        check(lib().mlb_km_assign(self._h, ctypes.byref(inertia), ctypes.byref(changed)))
+        return inertia.value, changed.value
+
+    def update(self):
+        shift = ctypes.c_double()
+        check(lib().mlb_km_update(self._h, ctypes.byref(shift)))
+        return shift.value
+
+    def get_labels(self):
+        labels = np.empty(self.n_local, dtype=np.uint32)
+        check(lib().mlb_km_get_labels(self._h, _ptr(labels)))
+        return labels
+
+    @property
+    def launch_count(self):
+        c = ctypes.c_int64()
+        check(lib().mlb_km_launch_count(self._h, ctypes.byref(c)))
+        return c.value
+
+    def close(self):
+        if self._h:
+            lib().mlb_km_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

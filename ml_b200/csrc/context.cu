@@ -44,26 +44,31 @@ struct VshardRanges {
     int64_t hi[kVirtualShards];
 };
 
-// out[v][e] = sum over the chunks of local virtual shard v of partials[c][e], in a fixed order:
-// four interleaved sequential accumulators combined as (a0+a1)+(a2+a3).
+// out[v][e] = sum over the chunks of local virtual shard v of partials[c][e], in a fixed order that
+// depends only on the shard's chunk list: 8 chunk lanes x 4 interleaved sequential accumulators,
+// combined as (a0+a1)+(a2+a3) per lane and then by a fixed tree over the lanes.  Block (32, 8).
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, VshardRanges r, int s, double* __restrict__ out)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
-    if (e >= s) return;
+    __shared__ double lanes[8][33];
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    const int v = blockIdx.y, ty = threadIdx.y;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    const int64_t lo = r.lo[v], hi = r.hi[v];
-    int64_t c = lo;
-    for (; c + 3 < hi; c += 4) {
-        a0 += partials[(c + 0) * s + e];
-        a1 += partials[(c + 1) * s + e];
-        a2 += partials[(c + 2) * s + e];
-        a3 += partials[(c + 3) * s + e];
+    if (e < s) {
+        const int64_t hi = r.hi[v];
+        for (int64_t c = r.lo[v] + 4 * ty; c < hi; c += 32) {
+            a0 += partials[c * s + e];
+            if (c + 1 < hi) a1 += partials[(c + 1) * s + e];
+            if (c + 2 < hi) a2 += partials[(c + 2) * s + e];
+            if (c + 3 < hi) a3 += partials[(c + 3) * s + e];
+        }
     }
-    if (c < hi) a0 += partials[c * s + e];
-    if (c + 1 < hi) a1 += partials[(c + 1) * s + e];
-    if (c + 2 < hi) a2 += partials[(c + 2) * s + e];
-    out[static_cast<int64_t>(v) * s + e] = (a0 + a1) + (a2 + a3);
+    lanes[ty][threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && e < s) {
+        const int x = threadIdx.x;
+        out[static_cast<int64_t>(v) * s + e] =
+            ((lanes[0][x] + lanes[1][x]) + (lanes[2][x] + lanes[3][x])) + ((lanes[4][x] + lanes[5][x]) + (lanes[6][x] + lanes[7][x]));
+    }
 }
 
 int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s)
@@ -78,8 +83,8 @@ int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, co
             r.lo[j] = data->lay.vshard_chunk[v] - sh.chunk_begin;
             r.hi[j] = data->lay.vshard_chunk[v + 1] - sh.chunk_begin;
         }
-        dim3 grid((s + 255) / 256, vpg);
-        reduce_partials_kernel<<<grid, 256, 0, gpu.stream>>>(partials[g], r, s, vsum[g] + static_cast<int64_t>(gpu.rank) * vpg * s);
+        dim3 grid((s + 31) / 32, vpg);
+        reduce_partials_kernel<<<grid, dim3(32, 8), 0, gpu.stream>>>(partials[g], r, s, vsum[g] + static_cast<int64_t>(gpu.rank) * vpg * s);
         MLB_CUDA(cudaGetLastError());
         return MLB_OK;
     }));

@@ -1,0 +1,915 @@
+// Gaussian-mixture EM on B200 (sm_100a), FP64.  Replaces the loops of ML/EM.cpp:
+//     expectation_step   EM.cpp:190-219      maximisation_step   EM.cpp:221-263
+//     process_covariances EM.cpp:274-287     calculate_labels    EM.cpp:289-304
+//     calculate_sample_covariance EM.cpp:265-272
+//
+// Formulation (DESIGN.md "EM kernels").  With z = x - c (c = the global data mean, held per data
+// set) every point has a feature vector phi(z) = [1, z_a, z_a z_b (a <= b)].  Then
+//   E-step:  log(pi_k N_k(x)) + D/2 log(2 pi) = phi(z) . theta_k        -- a [points x F] x [F x K] product
+//   M-step:  S[f][k] = sum_i phi_f(z_i) r_ik                             -- a [F x points] x [points x K] product
+// where theta_k packs -1/2 Sigma_k^-1, Sigma_k^-1 (mu_k - c) and the constant, and S packs the
+// weighted count, first and second moments about c.  Both products run on the FP64 tensor pipe
+// (mma.sync.m8n8k4.f64 -> DMMA.8x8x4), the features are generated in registers from the point
+// tile in shared memory, and the responsibilities never leave the SM.  One fused kernel per
+// iteration reads X exactly once.
+//
+// Determinism: per-chunk partial statistics in a fixed layout, chunks are a function of N only,
+// fixed-order reduction (context.cu), no floating-point atomics anywhere.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "internal.h"
+
+namespace mlb {
+
+constexpr int kTile = 64;        // points per CTA tile
+constexpr int kEmThreads = 128;  // 4 warps
+
+// ---- compile-time shape helpers -------------------------------------------------------------
+// E-step contraction steps (4 features each): for a in [0,DP), for m in [a/4, DP/4): lane c holds
+// z_a * z_{4m+c}; then DP/4 linear steps: lane c holds z_{4m+c}.
+__host__ __device__ constexpr int em_estep_index(int DP, int a, int m)
+{
+    int n = 0;
+    for (int i = 0; i < a; ++i) n += DP / 4 - i / 4;
+    return n + (m - a / 4);
+}
+__host__ __device__ constexpr int em_ne(int DP) { return em_estep_index(DP, DP - 1, DP / 4 - 1) + 1 + DP / 4; }
+// M-step features: 1, z_a, z_a z_b (a <= b), padded to a multiple of 8 rows.
+__host__ __device__ constexpr int em_fm_raw(int DP) { return 1 + DP + DP * (DP + 1) / 2; }
+__host__ __device__ constexpr int em_nm(int DP) { return (em_fm_raw(DP) + 7) / 8; }
+__host__ __device__ constexpr int em_sv(int DP, int KP) { return em_nm(DP) * 8 * KP + 8; }
+__host__ __device__ constexpr int em_theta_len(int DP, int KP) { return em_ne(DP) * (KP / 8) * 32 + KP; }
+
+constexpr size_t em_smem_bytes(int DP, int KP)
+{
+    return sizeof(double) * (em_theta_len(DP, KP) + 2 * kTile * (DP + 4) + kTile * (KP + 4) + 8 + DP);
+}
+
+struct EmArgs {
+    const double* x;       // local points, d doubles each
+    long long n_local;
+    int d, k;
+    const double* shift;   // d
+    const double* theta;   // E-step image: [NE][NT/2][32 lanes][2] (or [NE][32] for NT == 1), then KP constants
+    const int2* feat_m;    // [NM*8] Z-row offsets (ia, ib) of each M-step feature
+    double* partials;      // [n_chunks][SV]
+    int chunk;             // points per chunk
+    int n_chunks;
+    unsigned* counter;     // dynamic chunk scheduler
+    const double* r_in;    // MODE 1: responsibilities, column-major local rows
+    long long r_ld;
+    double* r_out;         // MODE 2: responsibilities of [range_begin, range_begin + range_count), column-major
+    long long r_out_ld;
+    unsigned* labels_out;  // MODE 2
+    long long range_begin, range_count;
+};
+
+__device__ __forceinline__ long long min64(long long a, long long b) { return a < b ? a : b; }
+
+__device__ __forceinline__ void dmma(double (&acc)[2], double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[0]), "+d"(acc[1]) : "d"(a), "d"(b));
+}
+
+template <int NT>
+__device__ __forceinline__ void load_theta_frag(const double* thE, int j, int lane, double (&bf)[NT])
+{
+    if constexpr (NT == 1) {
+        bf[0] = thE[j * 32 + lane];
+    } else {
+#pragma unroll
+        for (int h = 0; h < NT / 2; ++h) {
+            const double2 v = reinterpret_cast<const double2*>(thE)[(j * (NT / 2) + h) * 32 + lane];
+            bf[2 * h] = v.x;
+            bf[2 * h + 1] = v.y;
+        }
+    }
+}
+
+// MODE 0: fused E+M step.  MODE 1: M-step from given responsibilities.  MODE 2: E-step only,
+// writing responsibilities and labels (the "emit" pass).
+template <int DP, int KP, int MODE>
+__global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 : 2) em_kernel(const EmArgs p)
+{
+    constexpr int NT = KP / 8, DQ = DP / 4, NE = em_ne(DP), NM = em_nm(DP);
+    constexpr int ZS = DP + 4, RS = KP + 4;
+    constexpr int WN = (NM >= 8 || NT == 1) ? 1 : 2, WM = 4 / WN;
+    constexpr int MW = (NM + WM - 1) / WM, NW = NT / WN;
+    constexpr int SV = em_sv(DP, KP);
+    constexpr int XR = kTile * DP / kEmThreads;
+
+    extern __shared__ __align__(16) double sm[];
+    double* thE = sm;
+    double* cE = thE + NE * NT * 32;
+    double* Zb = cE + KP;
+    double* R = Zb + 2 * kTile * ZS;
+    double* wl = R + kTile * RS;
+    double* sh = wl + 8;
+    __shared__ int s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+    const int d = p.d;
+
+    if (MODE != 1)
+        for (int i = tid; i < em_theta_len(DP, KP); i += kEmThreads) sm[i] = p.theta[i];
+    for (int i = tid; i < 2 * kTile * ZS; i += kEmThreads) Zb[i] = 0.0;
+    for (int i = tid; i < kTile * RS; i += kEmThreads) R[i] = 0.0;
+    if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
+
+    // M-step ownership: warp (wm, wn) holds feature tiles wm*MW .. wm*MW+MW-1 x component tiles wn*NW .. +NW-1.
+    const int wm = warp / WN, wn = warp % WN;
+    int ia[MW], ib[MW];
+    double sacc[MW][NW][2];
+    if (MODE != 2) {
+#pragma unroll
+        for (int i = 0; i < MW; ++i) {
+            const int mt = wm * MW + i;
+            const int2 f = mt < NM ? p.feat_m[mt * 8 + g] : make_int2(DP + 1, DP + 1);
+            ia[i] = f.x;
+            ib[i] = f.y;
+        }
+    }
+
+    double xr[XR];
+    auto load_tile = [&](long long point0, int nvalid) {
+        const double* xg = p.x + point0 * d;
+        const int nel = nvalid * d;
+#pragma unroll
+        for (int r = 0; r < XR; ++r) {
+            const int e = tid + kEmThreads * r;
+            xr[r] = e < nel ? xg[e] : 0.0;
+        }
+    };
+    auto store_tile = [&](double* Z, int nvalid) {
+        const int nel = nvalid * d;
+#pragma unroll
+        for (int r = 0; r < XR; ++r) {
+            const int e = tid + kEmThreads * r;
+            if (e < kTile * d) {
+                const int pt = (d == DP) ? e / DP : e / d;
+                const int dm = e - pt * d;
+                Z[pt * ZS + dm] = e < nel ? xr[r] - sh[dm] : 0.0;
+            }
+        }
+        if (tid < kTile) Z[tid * ZS + DP] = tid < nvalid ? 1.0 : 0.0;
+    };
+
+    const long long work_begin = MODE == 2 ? p.range_begin : 0;
+    const long long work_end = MODE == 2 ? p.range_begin + p.range_count : p.n_local;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = static_cast<int>(atomicAdd(p.counter, 1u));
+        __syncthreads();
+        const int chunk = s_next;
+        if (chunk >= p.n_chunks) break;
+        const long long p_begin = work_begin + static_cast<long long>(chunk) * p.chunk;
+        const long long p_end = min64(p_begin + p.chunk, work_end);
+        const int ntiles = static_cast<int>((p_end - p_begin + kTile - 1) / kTile);
+
+        if (MODE != 2) {
+#pragma unroll
+            for (int i = 0; i < MW; ++i)
+#pragma unroll
+                for (int nt = 0; nt < NW; ++nt) sacc[i][nt][0] = sacc[i][nt][1] = 0.0;
+        }
+        double ll_acc = 0.0;
+
+        load_tile(p_begin, static_cast<int>(min64(kTile, p_end - p_begin)));
+        store_tile(Zb, static_cast<int>(min64(kTile, p_end - p_begin)));
+        __syncthreads();
+
+        for (int t = 0; t < ntiles; ++t) {
+            double* Z = Zb + (t & 1) * kTile * ZS;
+            const long long tile0 = p_begin + static_cast<long long>(t) * kTile;
+            const int nvalid = static_cast<int>(min64(kTile, p_end - tile0));
+            const int nvalid_next = t + 1 < ntiles ? static_cast<int>(min64(kTile, p_end - tile0 - kTile)) : 0;
+            if (t + 1 < ntiles) load_tile(tile0 + kTile, nvalid_next);
+
+            if (MODE == 1) {
+                // responsibilities given by the caller (maximise_first, EM.cpp:120-125)
+                for (int idx = tid; idx < kTile * p.k; idx += kEmThreads) {
+                    const int pt = idx % kTile, kk = idx / kTile;
+                    R[pt * RS + kk] = pt < nvalid ? p.r_in[tile0 + pt + kk * p.r_ld] : 0.0;
+                }
+            } else {
+                // ---------------- E-step: Q = Phi(Z) . Theta for this warp's 16 points x all components
+                const double* z0 = Z + (warp * 16 + g) * ZS;
+                const double* z1 = z0 + 8 * ZS;
+                double acc[2][NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double2 cc = *reinterpret_cast<const double2*>(cE + 8 * nt + 2 * c);
+                    acc[0][nt][0] = acc[1][nt][0] = cc.x;
+                    acc[0][nt][1] = acc[1][nt][1] = cc.y;
+                }
+                double zc0[DQ], zc1[DQ];
+#pragma unroll
+                for (int m = 0; m < DQ; ++m) {
+                    zc0[m] = z0[4 * m + c];
+                    zc1[m] = z1[4 * m + c];
+                }
+#pragma unroll
+                for (int a = 0; a < DP; ++a) {
+                    const double za0 = z0[a], za1 = z1[a];
+#pragma unroll
+                    for (int m = a / 4; m < DQ; ++m) {
+                        double bf[NT];
+                        load_theta_frag<NT>(thE, em_estep_index(DP, a, m), lane, bf);
+                        const double a0 = za0 * zc0[m], a1 = za1 * zc1[m];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            dmma(acc[0][nt], a0, bf[nt]);
+                            dmma(acc[1][nt], a1, bf[nt]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < DQ; ++m) {
+                    double bf[NT];
+                    load_theta_frag<NT>(thE, NE - DQ + m, lane, bf);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        dmma(acc[0][nt], zc0[m], bf[nt]);
+                        dmma(acc[1][nt], zc1[m], bf[nt]);
+                    }
+                }
+                // ---------------- log-sum-exp over the 4 lanes that share a point
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int pl = warp * 16 + mt * 8 + g;
+                    double mx = -INFINITY;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mx = fmax(mx, fmax(acc[mt][nt][0], acc[mt][nt][1]));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    double sum = 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        acc[mt][nt][0] = exp(acc[mt][nt][0] - mx);
+                        acc[mt][nt][1] = exp(acc[mt][nt][1] - mx);
+                        sum += acc[mt][nt][0] + acc[mt][nt][1];
+                    }
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                    const double inv = 1.0 / sum;
+                    if (c == 0 && pl < nvalid) ll_acc += mx + log(sum);
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+                            *reinterpret_cast<double2*>(R + pl * RS + 8 * nt + 2 * c) = make_double2(acc[mt][nt][0] * inv, acc[mt][nt][1] * inv);
+                    } else {
+                        // emit: responsibilities_ (EM.cpp:213-218) and labels_ (EM.cpp:289-304, first maximum wins)
+                        double best = -1.0;
+                        unsigned best_k = 0xffffffffu;
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int kk = 8 * nt + 2 * c + e;
+                                const double r = acc[mt][nt][e] * inv;
+                                if (kk < p.k) {
+                                    if (pl < nvalid && p.r_out) p.r_out[(tile0 - p.range_begin) + pl + kk * p.r_out_ld] = r;
+                                    if (r > best) { best = r; best_k = kk; }
+                                }
+                            }
+#pragma unroll
+                        for (int off = 1; off <= 2; off <<= 1) {
+                            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                            const unsigned ok = __shfl_xor_sync(0xffffffffu, best_k, off);
+                            if (ob > best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+                        }
+                        if (c == 0 && pl < nvalid && p.labels_out) p.labels_out[(tile0 - p.range_begin) + pl] = best_k;
+                    }
+                }
+            }
+            if (MODE != 2) {
+                __syncthreads();
+                // ---------------- M-step: S += Phi(Z)^T . R over the tile's 64 points
+#pragma unroll 4
+                for (int s = 0; s < kTile / 4; ++s) {
+                    const double* zp = Z + (4 * s + c) * ZS;
+                    const double* rp = R + (4 * s + c) * RS + wn * NW * 8 + g;
+                    double bf[NW];
+#pragma unroll
+                    for (int nt = 0; nt < NW; ++nt) bf[nt] = rp[8 * nt];
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) {
+                        if (wm * MW + i < NM) {
+                            const double af = zp[ia[i]] * zp[ib[i]];
+#pragma unroll
+                            for (int nt = 0; nt < NW; ++nt) dmma(sacc[i][nt], af, bf[nt]);
+                        }
+                    }
+                }
+            }
+            if (t + 1 < ntiles) store_tile(Zb + ((t + 1) & 1) * kTile * ZS, nvalid_next);
+            __syncthreads();
+        }
+
+        if (MODE != 2) {
+            double* out = p.partials + static_cast<long long>(chunk) * SV;
+#pragma unroll
+            for (int i = 0; i < MW; ++i) {
+                const int mt = wm * MW + i;
+                if (mt < NM) {
+#pragma unroll
+                    for (int nt = 0; nt < NW; ++nt)
+                        *reinterpret_cast<double2*>(out + (mt * 8 + g) * KP + (wn * NW + nt) * 8 + 2 * c) = make_double2(sacc[i][nt][0], sacc[i][nt][1]);
+                }
+            }
+            // log-likelihood partial: fixed butterfly inside the warp, fixed order across warps
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) ll_acc += __shfl_xor_sync(0xffffffffu, ll_acc, off);
+            if (lane == 0) wl[warp] = ll_acc;
+            __syncthreads();
+            if (tid == 0) out[NM * 8 * KP] = (wl[0] + wl[1]) + (wl[2] + wl[3]);
+            if (tid >= 1 && tid < 8) out[NM * 8 * KP + tid] = 0.0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- parameter refresh (replicated on every GPU)
+//
+// One block per (padded) component.  Stage 1 (vsum != nullptr): fixed-tree sum of the 8 virtual
+// shard vectors, then mean / covariance / weight (EM.cpp:238-257) from moments about the shift c:
+//     mu = c + m1/s,   Sigma = m2/s - (m1/s)(m1/s)^T + 1e-15 I,   pi = s/N.
+// Stage 2: process_covariances (EM.cpp:274-287): Cholesky, inverse by solving against the identity,
+// sqrt|Sigma| = prod L_ii; then the E-step image theta for the next iteration.
+struct EmFinalizeArgs {
+    const double* vsum;   // [8][SV] or nullptr
+    const double* shift;
+    int d, k, DP, KP, SV;
+    long long n_total;
+    const int2* feat_m;   // [NM*8]
+    const int2* feat_e;   // [NE*4]: (a, b); b == DP: linear term a; a < 0: unused slot
+    int nm8, ne;
+    double* means;        // D x K
+    double* covs;         // K x (D x D)
+    double* weights;      // K
+    double* inv_covs;     // K x (D x D)
+    double* sqrt_dets;    // K
+    double* theta_out;    // E-step image
+    double* ll_out;       // log-likelihood of the E-step whose statistics these are (nullptr: skip)
+};
+
+__global__ void em_finalize_kernel(const EmFinalizeArgs p)
+{
+    extern __shared__ double fs[];
+    const int d = p.d, DP = p.DP, KP = p.KP, NT = KP / 8;
+    double* A = fs;            // covariance, column-major d x d
+    double* L = A + d * d;     // Cholesky factor (lower)
+    double* P = L + d * d;     // inverse covariance
+    double* delta = P + d * d; // mean - shift
+    double* m1 = delta + d;
+    double* v = m1 + d;        // P delta
+    __shared__ double s_count, s_const;
+    const int kc = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const bool real = kc < p.k;
+    double weight = 0.0;
+
+    if (real) {
+        if (p.vsum) {
+            for (int f = tid; f < p.nm8; f += nthr) {
+                const int2 ab = p.feat_m[f];
+                const double val = tree8(p.vsum + static_cast<long long>(f) * KP + kc, p.SV);
+                if (ab.x == DP && ab.y == DP) s_count = val;
+                else if (ab.y == DP && ab.x < d) m1[ab.x] = val;
+                else if (ab.x < d && ab.y < d) { A[ab.x + ab.y * d] = val; A[ab.y + ab.x * d] = val; }
+            }
+            __syncthreads();
+            const double s = s_count;
+            for (int a = tid; a < d; a += nthr) delta[a] = m1[a] / s;
+            __syncthreads();
+            for (int e = tid; e < d * d; e += nthr) {
+                const int a = e % d, b = e / d;
+                double cv = A[e] / s - delta[a] * delta[b];
+                if (a == b) cv += 1e-15;   // EM.cpp:250-256
+                A[e] = cv;
+                p.covs[static_cast<long long>(kc) * d * d + e] = cv;
+            }
+            weight = s / static_cast<double>(p.n_total);
+            for (int a = tid; a < d; a += nthr) p.means[a + kc * d] = p.shift[a] + delta[a];
+            if (tid == 0) p.weights[kc] = weight;
+        } else {
+            for (int e = tid; e < d * d; e += nthr) A[e] = p.covs[static_cast<long long>(kc) * d * d + e];
+            for (int a = tid; a < d; a += nthr) delta[a] = p.means[a + kc * d] - p.shift[a];
+            weight = p.weights[kc];
+        }
+        __syncthreads();
+        // Unblocked left-looking Cholesky, sequential inner sums (same order as the oracle's restatement of Eigen::LLT).
+        for (int e = tid; e < d * d; e += nthr) L[e] = A[e];
+        __syncthreads();
+        for (int j = 0; j < d; ++j) {
+            if (tid == 0) {
+                double x = L[j + j * d];
+                double sq = 0.0;
+                for (int t = 0; t < j; ++t) sq += L[j + t * d] * L[j + t * d];
+                if (j > 0) x -= sq;
+                L[j + j * d] = sqrt(x);
+            }
+            __syncthreads();
+            const double ljj = L[j + j * d];
+            for (int i = j + 1 + tid; i < d; i += nthr) {
+                double dot = 0.0;
+                for (int t = 0; t < j; ++t) dot += L[i + t * d] * L[j + t * d];
+                double val = L[i + j * d];
+                if (j > 0) val -= dot;
+                L[i + j * d] = val / ljj;
+            }
+            __syncthreads();
+        }
+        // llt.solve(Identity): forward then backward substitution, one column per thread.
+        for (int col = tid; col < d; col += nthr) {
+            double* x = P + col * d;
+            for (int i = 0; i < d; ++i) x[i] = i == col ? 1.0 : 0.0;
+            for (int i = 0; i < d; ++i) {
+                double val = x[i];
+                for (int j = 0; j < i; ++j) val -= L[i + j * d] * x[j];
+                x[i] = val / L[i + i * d];
+            }
+            for (int i = d - 1; i >= 0; --i) {
+                double val = x[i];
+                for (int j = i + 1; j < d; ++j) val -= L[j + i * d] * x[j];
+                x[i] = val / L[i + i * d];
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < d * d; e += nthr) p.inv_covs[static_cast<long long>(kc) * d * d + e] = P[e];
+        // v = P_sym delta using the upper triangle only, as xAx_symmetric does (LinearAlgebra.cpp:17-29)
+        for (int a = tid; a < d; a += nthr) {
+            double acc = 0.0;
+            for (int b = 0; b < d; ++b) acc += (b >= a ? P[a + b * d] : P[b + a * d]) * delta[b];
+            v[a] = acc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double sqrt_det = 1.0;
+            for (int i = 0; i < d; ++i) sqrt_det *= L[i + i * d];
+            p.sqrt_dets[kc] = sqrt_det;
+            double dv = 0.0;
+            for (int a = 0; a < d; ++a) dv += delta[a] * v[a];
+            s_const = log(weight / sqrt_det) - 0.5 * dv;
+        }
+        __syncthreads();
+    }
+    // E-step image
+    const int nt = kc / 8, row = kc % 8;
+    for (int idx = tid; idx < p.ne * 4; idx += nthr) {
+        const int j = idx >> 2, c = idx & 3;
+        const int2 ab = p.feat_e[idx];
+        double val = 0.0;
+        if (real && ab.x >= 0 && ab.x < d) {
+            if (ab.y == DP) val = v[ab.x];
+            else if (ab.y < d) val = ab.x == ab.y ? -0.5 * P[ab.x + ab.x * d] : -P[ab.x + ab.y * d];
+        }
+        const int lane = row * 4 + c;
+        if (NT == 1) p.theta_out[j * 32 + lane] = val;
+        else p.theta_out[((j * (NT / 2) + nt / 2) * 32 + lane) * 2 + (nt & 1)] = val;
+    }
+    if (tid == 0) p.theta_out[p.ne * NT * 32 + kc] = real ? s_const : -INFINITY;
+    if (p.ll_out && p.vsum && kc == 0 && tid == 0) {
+        const double ll_sum = tree8(p.vsum + (p.SV - 8), p.SV);
+        // mean over points minus D log(2 pi) / 2 (EM.cpp:197-211)
+        *p.ll_out = ll_sum / static_cast<double>(p.n_total) - 0.5 * d * log(2.0 * 3.14159265358979323846);
+    }
+}
+
+// ---------------------------------------------------------------- dispatch
+
+using EmKernelFn = void (*)(EmArgs);
+
+template <int MODE>
+static EmKernelFn em_kernel_for(int DP, int KP)
+{
+#define MLB_EM_CASE(D_, K_) if (DP == D_ && KP == K_) return em_kernel<D_, K_, MODE>;
+    MLB_EM_CASE(4, 8) MLB_EM_CASE(4, 16) MLB_EM_CASE(4, 32)
+    MLB_EM_CASE(8, 8) MLB_EM_CASE(8, 16) MLB_EM_CASE(8, 32)
+    MLB_EM_CASE(16, 8) MLB_EM_CASE(16, 16) MLB_EM_CASE(16, 32)
+#undef MLB_EM_CASE
+    return nullptr;
+}
+
+struct EmGpu {
+    double* theta[2] = {nullptr, nullptr};
+    double* params = nullptr;  // means | covs | weights | inv_covs | sqrt_dets
+    double* partials = nullptr;
+    double* vsum = nullptr;
+    double* ll = nullptr;      // ring of log-likelihoods
+    int2* feat_m = nullptr;
+    int2* feat_e = nullptr;
+    unsigned* counter = nullptr;
+    double* stage = nullptr;   // emit / responsibilities staging
+    unsigned* stage_labels = nullptr;
+    int grid = 0;
+};
+
+constexpr int kLlRing = 4096;
+constexpr long long kStagePoints = 1 << 20;
+
+}  // namespace mlb
+
+using namespace mlb;
+
+struct mlb_em {
+    mlb_ctx* ctx = nullptr;
+    mlb_data* data = nullptr;
+    int d = 0, k = 0, DP = 0, KP = 0, NT = 0, NE = 0, NM = 0, SV = 0;
+    std::vector<int2> feat_m, feat_e;
+    std::vector<EmGpu> gpus;
+    int cur = 0;
+    bool have_params = false, have_step = false;
+    int last_path = 0;
+    int64_t launches = 0;
+    int64_t steps_done = 0;
+    EmKernelFn fn_step = nullptr, fn_mstep = nullptr, fn_emit = nullptr;
+
+    double* means(int g) const { return gpus[g].params; }
+    double* covs(int g) const { return gpus[g].params + d * k; }
+    double* weights(int g) const { return covs(g) + static_cast<size_t>(k) * d * d; }
+    double* inv_covs(int g) const { return weights(g) + k; }
+    double* sqrt_dets(int g) const { return inv_covs(g) + static_cast<size_t>(k) * d * d; }
+    size_t params_len() const { return static_cast<size_t>(d) * k + 2 * static_cast<size_t>(k) * d * d + 2 * k; }
+};
+
+namespace mlb {
+
+static int pad_to(int v, const int* options, int n)
+{
+    for (int i = 0; i < n; ++i)
+        if (v <= options[i]) return options[i];
+    return 0;
+}
+
+static EmArgs base_args(const mlb_em* em, int g)
+{
+    const DataShard& sh = em->data->shards[g];
+    const EmGpu& eg = em->gpus[g];
+    EmArgs a{};
+    a.x = sh.x;
+    a.n_local = sh.n();
+    a.d = em->d;
+    a.k = em->k;
+    a.shift = sh.shift;
+    a.theta = eg.theta[em->cur];
+    a.feat_m = eg.feat_m;
+    a.partials = eg.partials;
+    a.chunk = em->data->lay.chunk;
+    a.n_chunks = static_cast<int>(sh.n_chunks());
+    a.counter = eg.counter;
+    return a;
+}
+
+static int launch_em(mlb_em* em, EmKernelFn fn, const EmArgs& a, int g, int grid)
+{
+    Gpu& gpu = em->ctx->gpus[g];
+    MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
+    if (a.n_chunks > 0) {
+        fn<<<std::min(grid, a.n_chunks), kEmThreads, em_smem_bytes(em->DP, em->KP), gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        ++em->launches;
+    }
+    return MLB_OK;
+}
+
+static EmFinalizeArgs finalize_args(const mlb_em* em, int g, bool from_stats, int theta_slot, double* ll_out)
+{
+    const EmGpu& eg = em->gpus[g];
+    EmFinalizeArgs f{};
+    f.vsum = from_stats ? eg.vsum : nullptr;
+    f.shift = em->data->shards[g].shift;
+    f.d = em->d; f.k = em->k; f.DP = em->DP; f.KP = em->KP; f.SV = em->SV;
+    f.n_total = em->data->lay.n_total;
+    f.feat_m = eg.feat_m; f.feat_e = eg.feat_e;
+    f.nm8 = em->NM * 8; f.ne = em->NE;
+    f.means = em->means(g); f.covs = em->covs(g); f.weights = em->weights(g);
+    f.inv_covs = em->inv_covs(g); f.sqrt_dets = em->sqrt_dets(g);
+    f.theta_out = eg.theta[theta_slot];
+    f.ll_out = ll_out;
+    return f;
+}
+
+static int launch_finalize(mlb_em* em, int g, bool from_stats, int theta_slot, double* ll_out)
+{
+    const EmFinalizeArgs f = finalize_args(em, g, from_stats, theta_slot, ll_out);
+    const size_t smem = sizeof(double) * (3 * em->d * em->d + 3 * em->d);
+    em_finalize_kernel<<<em->KP, 128, smem, em->ctx->gpus[g].stream>>>(f);
+    MLB_CUDA(cudaGetLastError());
+    ++em->launches;
+    return MLB_OK;
+}
+
+// E+M over all local points, statistics reduced and exchanged, parameters refreshed into the other theta slot.
+static int enqueue_step(mlb_em* em)
+{
+    mlb_ctx* ctx = em->ctx;
+    const int ll_slot = static_cast<int>(em->steps_done % kLlRing);
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+        return launch_em(em, em->fn_step, base_args(em, g), g, em->gpus[g].grid);
+    }));
+    std::vector<double*> partials, vsum;
+    for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
+    MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV));
+    em->launches += static_cast<int64_t>(ctx->gpus.size());
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+        return launch_finalize(em, g, true, em->cur ^ 1, em->gpus[g].ll + ll_slot);
+    }));
+    em->cur ^= 1;
+    return MLB_OK;
+}
+
+}  // namespace mlb
+
+extern "C" {
+
+int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
+{
+    MLB_REQUIRE(ctx && data && out, "mlb_em_create: null argument");
+    MLB_REQUIRE(data->ctx == ctx, "mlb_em_create: data belongs to another context");
+    MLB_REQUIRE(k >= 1, "mlb_em_create: number of components must be positive");
+    static const int dps[] = {4, 8, 16}, kps[] = {8, 16, 32};
+    const int DP = pad_to(data->d, dps, 3), KP = pad_to(k, kps, 3);
+    MLB_REQUIRE(DP && KP, "mlb_em_create: D=%d, K=%d not supported by this build (D <= 16, K <= 32)", data->d, k);
+    auto* em = new mlb_em;
+    em->ctx = ctx; em->data = data; em->d = data->d; em->k = k;
+    em->DP = DP; em->KP = KP; em->NT = KP / 8; em->NE = em_ne(DP); em->NM = em_nm(DP); em->SV = em_sv(DP, KP);
+    em->fn_step = em_kernel_for<0>(DP, KP);
+    em->fn_mstep = em_kernel_for<1>(DP, KP);
+    em->fn_emit = em_kernel_for<2>(DP, KP);
+    // E-step slots, in the order the kernel enumerates them.
+    em->feat_e.assign(static_cast<size_t>(em->NE) * 4, make_int2(-1, -1));
+    for (int a = 0; a < DP; ++a)
+        for (int m = a / 4; m < DP / 4; ++m)
+            for (int c = 0; c < 4; ++c) {
+                const int b = 4 * m + c;
+                if (b >= a) em->feat_e[em_estep_index(DP, a, m) * 4 + c] = make_int2(a, b);
+            }
+    for (int m = 0; m < DP / 4; ++m)
+        for (int c = 0; c < 4; ++c) em->feat_e[(em->NE - DP / 4 + m) * 4 + c] = make_int2(4 * m + c, DP);
+    // M-step features as offsets into a Z row: [0,DP) coordinates, DP the constant 1, DP+1 a zero.
+    em->feat_m.assign(static_cast<size_t>(em->NM) * 8, make_int2(DP + 1, DP + 1));
+    {
+        size_t f = 0;
+        em->feat_m[f++] = make_int2(DP, DP);
+        for (int a = 0; a < DP; ++a) em->feat_m[f++] = make_int2(a, DP);
+        for (int a = 0; a < DP; ++a)
+            for (int b = a; b < DP; ++b) em->feat_m[f++] = make_int2(a, b);
+    }
+    em->gpus.resize(ctx->gpus.size());
+    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        EmGpu& eg = em->gpus[g];
+        const DataShard& sh = data->shards[g];
+        const size_t theta_len = em_theta_len(DP, KP);
+        MLB_CUDA(cudaMalloc(&eg.theta[0], sizeof(double) * theta_len));
+        MLB_CUDA(cudaMalloc(&eg.theta[1], sizeof(double) * theta_len));
+        MLB_CUDA(cudaMalloc(&eg.params, sizeof(double) * em->params_len()));
+        MLB_CUDA(cudaMalloc(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV));
+        MLB_CUDA(cudaMalloc(&eg.vsum, sizeof(double) * kVirtualShards * em->SV));
+        MLB_CUDA(cudaMalloc(&eg.ll, sizeof(double) * kLlRing));
+        MLB_CUDA(cudaMalloc(&eg.feat_m, sizeof(int2) * em->feat_m.size()));
+        MLB_CUDA(cudaMalloc(&eg.feat_e, sizeof(int2) * em->feat_e.size()));
+        MLB_CUDA(cudaMalloc(&eg.counter, sizeof(unsigned)));
+        MLB_CUDA(cudaMemsetAsync(eg.vsum, 0, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(eg.feat_m, em->feat_m.data(), sizeof(int2) * em->feat_m.size(), cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(eg.feat_e, em->feat_e.data(), sizeof(int2) * em->feat_e.size(), cudaMemcpyHostToDevice, gpu.stream));
+        const size_t smem = em_smem_bytes(DP, KP);
+        for (EmKernelFn fn : {em->fn_step, em->fn_mstep, em->fn_emit})
+            MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int per_sm = 0, sms = 0;
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(em->fn_step), kEmThreads, smem));
+        MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
+        MLB_REQUIRE(per_sm >= 1, "mlb_em_create: EM kernel does not fit on an SM");
+        eg.grid = per_sm * sms;
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    });
+    if (rc != MLB_OK) { mlb_em_destroy(em); return rc; }
+    *out = em;
+    return MLB_OK;
+}
+
+int mlb_em_destroy(mlb_em* em)
+{
+    if (!em) return MLB_OK;
+    for (size_t g = 0; g < em->gpus.size(); ++g) {
+        cudaSetDevice(em->ctx->gpus[g].device);
+        cudaStreamSynchronize(em->ctx->gpus[g].stream);
+        EmGpu& eg = em->gpus[g];
+        for (void* ptr : {static_cast<void*>(eg.theta[0]), static_cast<void*>(eg.theta[1]), static_cast<void*>(eg.params),
+                          static_cast<void*>(eg.partials), static_cast<void*>(eg.vsum), static_cast<void*>(eg.ll),
+                          static_cast<void*>(eg.feat_m), static_cast<void*>(eg.feat_e), static_cast<void*>(eg.counter),
+                          static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels)})
+            if (ptr) cudaFree(ptr);
+    }
+    delete em;
+    return MLB_OK;
+}
+
+int mlb_em_set_params(mlb_em* em, const double* means, const double* covariances, const double* weights)
+{
+    MLB_REQUIRE(em && means && covariances && weights, "mlb_em_set_params: null argument");
+    const size_t dk = static_cast<size_t>(em->d) * em->k, kdd = static_cast<size_t>(em->k) * em->d * em->d;
+    MLB_TRY(for_each_gpu(em->ctx, [&](int g, Gpu& gpu) -> int {
+        MLB_CUDA(cudaMemcpyAsync(em->means(g), means, sizeof(double) * dk, cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(em->covs(g), covariances, sizeof(double) * kdd, cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(em->weights(g), weights, sizeof(double) * em->k, cudaMemcpyHostToDevice, gpu.stream));
+        MLB_TRY(launch_finalize(em, g, false, em->cur, nullptr));
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));  // the host buffers may go away
+        return MLB_OK;
+    }));
+    em->have_params = true;
+    em->have_step = false;
+    return MLB_OK;
+}
+
+int mlb_em_run_steps(mlb_em* em, int steps, double* log_likelihoods)
+{
+    MLB_REQUIRE(em && steps >= 0, "mlb_em_run_steps: bad argument");
+    MLB_REQUIRE(steps <= kLlRing, "mlb_em_run_steps: at most %d steps per call", kLlRing);
+    if (!em->have_params) { set_error("mlb_em_run_steps: parameters not set"); return MLB_ESTATE; }
+    const int64_t first = em->steps_done;
+    for (int s = 0; s < steps; ++s) {
+        MLB_TRY(enqueue_step(em));
+        ++em->steps_done;
+    }
+    if (steps > 0) { em->have_step = true; em->last_path = 1; }
+    if (log_likelihoods) {
+        Gpu& gpu = em->ctx->gpus[0];
+        MLB_CUDA(cudaSetDevice(gpu.device));
+        for (int s = 0; s < steps; ++s)
+            MLB_CUDA(cudaMemcpyAsync(log_likelihoods + s, em->gpus[0].ll + (first + s) % kLlRing, sizeof(double), cudaMemcpyDeviceToHost, gpu.stream));
+    }
+    return mlb_ctx_synchronize(em->ctx);
+}
+
+int mlb_em_step(mlb_em* em, double* log_likelihood)
+{
+    MLB_REQUIRE(em && log_likelihood, "mlb_em_step: null argument");
+    return mlb_em_run_steps(em, 1, log_likelihood);
+}
+
+int mlb_em_get_params(mlb_em* em, double* means, double* covariances, double* weights)
+{
+    MLB_REQUIRE(em, "mlb_em_get_params: null argument");
+    if (!em->have_params) { set_error("mlb_em_get_params: parameters not set"); return MLB_ESTATE; }
+    Gpu& gpu = em->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    if (means) MLB_CUDA(cudaMemcpyAsync(means, em->means(0), sizeof(double) * em->d * em->k, cudaMemcpyDeviceToHost, gpu.stream));
+    if (covariances) MLB_CUDA(cudaMemcpyAsync(covariances, em->covs(0), sizeof(double) * em->k * em->d * em->d, cudaMemcpyDeviceToHost, gpu.stream));
+    if (weights) MLB_CUDA(cudaMemcpyAsync(weights, em->weights(0), sizeof(double) * em->k, cudaMemcpyDeviceToHost, gpu.stream));
+    MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+    return MLB_OK;
+}
+
+int mlb_em_get_precisions(mlb_em* em, double* inverse_covariances, double* sqrt_determinants)
+{
+    MLB_REQUIRE(em, "mlb_em_get_precisions: null argument");
+    if (!em->have_params) { set_error("mlb_em_get_precisions: parameters not set"); return MLB_ESTATE; }
+    Gpu& gpu = em->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    if (inverse_covariances)
+        MLB_CUDA(cudaMemcpyAsync(inverse_covariances, em->inv_covs(0), sizeof(double) * em->k * em->d * em->d, cudaMemcpyDeviceToHost, gpu.stream));
+    if (sqrt_determinants) MLB_CUDA(cudaMemcpyAsync(sqrt_determinants, em->sqrt_dets(0), sizeof(double) * em->k, cudaMemcpyDeviceToHost, gpu.stream));
+    MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+    return MLB_OK;
+}
+
+int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
+{
+    MLB_REQUIRE(em && cov_out, "mlb_em_sample_covariance: null argument");
+    // A one-component M-step with unit responsibilities: theta = 0 for component 0, -inf constants elsewhere.
+    // Uses the spare theta slot and leaves the current parameters untouched.
+    const int d = em->d, DP = em->DP, KP = em->KP;
+    std::vector<double> theta(em_theta_len(DP, KP), 0.0);
+    for (int kk = 1; kk < KP; ++kk) theta[static_cast<size_t>(em->NE) * em->NT * 32 + kk] = -std::numeric_limits<double>::infinity();
+    MLB_TRY(for_each_gpu(em->ctx, [&](int g, Gpu& gpu) -> int {
+        MLB_CUDA(cudaMemcpyAsync(em->gpus[g].theta[em->cur ^ 1], theta.data(), sizeof(double) * theta.size(), cudaMemcpyHostToDevice, gpu.stream));
+        EmArgs a = base_args(em, g);
+        a.theta = em->gpus[g].theta[em->cur ^ 1];
+        return launch_em(em, em->fn_step, a, g, em->gpus[g].grid);
+    }));
+    std::vector<double*> partials, vsum;
+    for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
+    MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV));
+    em->launches += static_cast<int64_t>(em->ctx->gpus.size());
+    std::vector<double> host(static_cast<size_t>(kVirtualShards) * em->SV);
+    Gpu& gpu0 = em->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu0.device));
+    MLB_CUDA(cudaMemcpyAsync(host.data(), em->gpus[0].vsum, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, gpu0.stream));
+    MLB_TRY(mlb_ctx_synchronize(em->ctx));
+    double count = 0;
+    std::vector<double> m1(d, 0.0), m2(static_cast<size_t>(d) * d, 0.0);
+    for (size_t f = 0; f < em->feat_m.size(); ++f) {
+        const int2 ab = em->feat_m[f];
+        const double val = tree8(host.data() + f * KP, em->SV);
+        if (ab.x == DP && ab.y == DP) count = val;
+        else if (ab.y == DP && ab.x < d) m1[ab.x] = val;
+        else if (ab.x < d && ab.y < d) { m2[ab.x + static_cast<size_t>(ab.y) * d] = val; m2[ab.y + static_cast<size_t>(ab.x) * d] = val; }
+    }
+    // unbiased covariance (EM.cpp:265-272): (sum z z^T - N dbar dbar^T) / (N - 1), z = x - c, dbar = mean(z) ~ 0
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b)
+            cov_out[a + static_cast<size_t>(b) * d] = (m2[a + static_cast<size_t>(b) * d] - m1[a] * m1[b] / count) / (count - 1.0);
+    return MLB_OK;
+}
+
+int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t ld)
+{
+    MLB_REQUIRE(em && resp, "mlb_em_mstep_from_responsibilities: null argument");
+    mlb_ctx* ctx = em->ctx;
+    const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
+    std::vector<double*> dev(ctx->gpus.size(), nullptr);
+    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        const DataShard& sh = em->data->shards[g];
+        const int64_t n = std::max<int64_t>(1, sh.n());
+        MLB_CUDA(cudaMalloc(&dev[g], sizeof(double) * n * em->k));
+        if (sh.n() > 0)
+            MLB_CUDA(cudaMemcpy2DAsync(dev[g], sizeof(double) * n, resp + (sh.begin - host_begin), sizeof(double) * ld, sizeof(double) * sh.n(),
+                                       em->k, cudaMemcpyHostToDevice, gpu.stream));
+        return MLB_OK;
+    });
+    if (rc == MLB_OK) {
+        rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+            EmArgs a = base_args(em, g);
+            a.r_in = dev[g];
+            a.r_ld = std::max<int64_t>(1, em->data->shards[g].n());  // device copy: local rows only
+            return launch_em(em, em->fn_mstep, a, g, em->gpus[g].grid);
+        });
+        if (rc == MLB_OK) {
+            std::vector<double*> partials, vsum;
+            for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
+            rc = reduce_and_exchange(em->data, partials, vsum, em->SV);
+            em->launches += static_cast<int64_t>(ctx->gpus.size());
+        }
+        if (rc == MLB_OK)
+            rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, true, em->cur, nullptr); });
+        if (rc == MLB_OK) rc = mlb_ctx_synchronize(ctx);
+    }
+    for (size_t g = 0; g < dev.size(); ++g)
+        if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFree(dev[g]); }
+    if (rc == MLB_OK) { em->have_params = true; em->have_step = false; }
+    return rc;
+}
+
+int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_out)
+{
+    MLB_REQUIRE(em, "mlb_em_emit: null argument");
+    if (!em->have_step) { set_error("mlb_em_emit: no step has been run"); return MLB_ESTATE; }
+    if (!resp_out && !labels_out) return MLB_OK;
+    mlb_ctx* ctx = em->ctx;
+    const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
+    // Stage by stage: kStagePoints points per GPU at a time through a device buffer.
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+        EmGpu& eg = em->gpus[g];
+        if (!eg.stage) MLB_CUDA(cudaMalloc(&eg.stage, sizeof(double) * kStagePoints * em->k));
+        if (!eg.stage_labels) MLB_CUDA(cudaMalloc(&eg.stage_labels, sizeof(unsigned) * kStagePoints));
+        return MLB_OK;
+    }));
+    int64_t longest = 0;
+    for (const DataShard& sh : em->data->shards) longest = std::max(longest, sh.n());
+    for (int64_t off = 0; off < longest; off += kStagePoints) {
+        MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+            const DataShard& sh = em->data->shards[g];
+            const int64_t count = std::min<int64_t>(kStagePoints, sh.n() - off);
+            if (count <= 0) return MLB_OK;
+            EmGpu& eg = em->gpus[g];
+            EmArgs a = base_args(em, g);
+            a.theta = eg.theta[em->cur ^ 1];  // theta_t of the last step
+            a.chunk = kTile;
+            a.n_chunks = static_cast<int>((count + kTile - 1) / kTile);
+            a.range_begin = off;
+            a.range_count = count;
+            a.r_out = resp_out ? eg.stage : nullptr;
+            a.r_out_ld = kStagePoints;
+            a.labels_out = labels_out ? eg.stage_labels : nullptr;
+            MLB_TRY(launch_em(em, em->fn_emit, a, g, 8 * kSmCount));
+            const int64_t row = sh.begin - host_begin + off;
+            if (resp_out)
+                MLB_CUDA(cudaMemcpy2DAsync(resp_out + row, sizeof(double) * ld, eg.stage, sizeof(double) * kStagePoints, sizeof(double) * count, em->k,
+                                           cudaMemcpyDeviceToHost, gpu.stream));
+            if (labels_out) MLB_CUDA(cudaMemcpyAsync(labels_out + row, eg.stage_labels, sizeof(unsigned) * count, cudaMemcpyDeviceToHost, gpu.stream));
+            return MLB_OK;
+        }));
+        MLB_TRY(mlb_ctx_synchronize(ctx));
+    }
+    return MLB_OK;
+}
+
+int mlb_em_last_path(const mlb_em* em, int* path)
+{
+    MLB_REQUIRE(em && path, "mlb_em_last_path: null argument");
+    *path = em->last_path;
+    return MLB_OK;
+}
+
+int mlb_em_launch_count(const mlb_em* em, int64_t* launches)
+{
+    MLB_REQUIRE(em && launches, "mlb_em_launch_count: null argument");
+    *launches = em->launches;
+    return MLB_OK;
+}
+
+}  // extern "C"

@@ -124,7 +124,7 @@ int for_each_gpu(mlb_ctx* ctx, F&& body)
 int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s);
 
 // Host-side fixed tree over the 8 virtual-shard vectors: ((0+1)+(2+3))+((4+5)+(6+7)).
-inline double tree8(const double* v, int64_t stride)
+__host__ __device__ inline double tree8(const double* v, int64_t stride)
 {
     return ((v[0] + v[stride]) + (v[2 * stride] + v[3 * stride])) + ((v[4 * stride] + v[5 * stride]) + (v[6 * stride] + v[7 * stride]));
 }

@@ -1,0 +1,558 @@
+// K-means (Lloyd) on B200 (sm_100a), FP64.  Replaces the loops of ML/KMeans.cpp:
+//     assignment_step + assign_label   KMeans.cpp:153-178
+//     update_step                      KMeans.cpp:180-192
+//
+// Assignment = filter + exact refinement (DESIGN.md "K-means kernels").
+//   filter:  score_ik = |c'_k|^2 - 2 z_i . c'_k  (z = x - shift, c' = c - shift) for all K centroids as
+//            a [points x D] x [D x K] product on the FP64 tensor pipe (mma.sync.m8n8k4.f64), tracking
+//            the best and second-best score per point;
+//   refine:  the winner's squared distance is recomputed exactly as the reference does
+//            ((x - c).squaredNorm(), sequential over the dimensions) so labels, distances and inertia are
+//            the reference's; a point whose two best scores are closer than the rounding bound of the
+//            filter is re-assigned by the exact scan over all K (strict <, lowest k wins).
+// Update statistics (per-cluster count and sum of z) are accumulated in shared memory by the warp
+// that owns the cluster, in point order: no floating-point atomics, bitwise reproducible.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "internal.h"
+
+namespace mlb {
+
+constexpr int kKmTile = 128;     // points per CTA tile
+constexpr int kKmThreads = 256;  // 8 warps, 16 points each
+constexpr int kKmGroup = 32;     // centroids per accumulator group (4 n-tiles)
+
+struct KmArgs {
+    const double* x;
+    long long n_local;
+    int d, k, KP;
+    const double* shift;
+    const double* cfrag;    // [DP/4][KP/16][32][2] image of -2 c'
+    const double* cnorm;    // [KP] |c'_k|^2 (+inf for padding)
+    const double* craw;     // D x K centroids as the host sees them
+    const double* cmax;     // [1] max_k |c'_k|
+    unsigned* labels;       // in: previous labels, out: new labels
+    double* partials;       // [n_chunks][SV]: K x (D+1) sums and counts, inertia, changed
+    int chunk, n_chunks;
+    unsigned* counter;
+    int accumulate;         // 0: labels / inertia only
+};
+
+__device__ __forceinline__ void km_dmma(double (&acc)[2], double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(acc[0]), "+d"(acc[1]) : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline int km_sv(int d, int KP) { return KP * (d + 1) + 8; }
+
+inline size_t km_smem_bytes(int DP, int d, int KP)
+{
+    return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + kKmTile * (DP + 4) + static_cast<size_t>(KP) * (d + 1) + DP + 16) + sizeof(int) * kKmTile;
+}
+
+// (x - c).squaredNorm() exactly as KMeans.cpp:158 evaluates it (sequential, fused multiply-add).
+__device__ __forceinline__ double exact_distance(const double* x, const double* c, int d)
+{
+    double s = 0.0;
+    for (int l = 0; l < d; ++l) {
+        const double t = x[l] - c[l];
+        s = fma(t, t, s);
+    }
+    return s;
+}
+
+template <int DP>
+__global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p)
+{
+    constexpr int DQ = DP / 4, XS = DP + 4;
+    extern __shared__ __align__(16) double sm[];
+    const int KP = p.KP, d = p.d, SD = d + 1;
+    double* Bf = sm;                                  // DP * KP
+    double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
+    double* X = nrm + KP;                             // kKmTile * XS, raw coordinates (padding columns zero)
+    double* sums = X + kKmTile * XS;                  // KP * (d+1)
+    double* sh = sums + static_cast<size_t>(KP) * SD; // DP
+    double* red = sh + DP;                            // 16
+    int* labs = reinterpret_cast<int*>(red + 16);     // kKmTile
+    __shared__ int s_next;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+
+    for (int i = tid; i < DP * KP + KP; i += kKmThreads) sm[i] = i < DP * KP ? p.cfrag[i] : p.cnorm[i - DP * KP];
+    for (int i = tid; i < kKmTile * XS; i += kKmThreads) X[i] = 0.0;
+    for (int i = tid; i < KP * SD; i += kKmThreads) sums[i] = 0.0;
+    if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
+    __syncthreads();
+    double shc[DQ];
+#pragma unroll
+    for (int j = 0; j < DQ; ++j) shc[j] = sh[4 * j + c];
+    const double u_bound = 8.0 * (d + 4) * 1.1102230246251565e-16;
+    const double cmax = *p.cmax;
+    const int own_lo = warp * (KP / 8), own_hi = own_lo + KP / 8;   // clusters whose statistics this warp accumulates
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = static_cast<int>(atomicAdd(p.counter, 1u));
+        __syncthreads();
+        const int chunk = s_next;
+        if (chunk >= p.n_chunks) break;
+        const long long p_begin = static_cast<long long>(chunk) * p.chunk;
+        const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
+        const int ntiles = static_cast<int>((p_end - p_begin + kKmTile - 1) / kKmTile);
+        double inertia_acc = 0.0;
+        int changed_acc = 0;
+
+        for (int t = 0; t < ntiles; ++t) {
+            const long long tile0 = p_begin + static_cast<long long>(t) * kKmTile;
+            const int nvalid = static_cast<int>(p_end - tile0 < kKmTile ? p_end - tile0 : kKmTile);
+            {
+                const double* xg = p.x + tile0 * d;
+                const int nel = nvalid * d;
+                for (int e = tid; e < kKmTile * d; e += kKmThreads) {
+                    const int pt = e / d, dm = e - pt * d;
+                    X[pt * XS + dm] = e < nel ? xg[e] : 0.0;
+                }
+            }
+            __syncthreads();
+
+            // ---------------- filter: scores of this warp's 16 points against all centroids
+            const double* x0 = X + (warp * 16 + g) * XS;
+            const double* x1 = x0 + 8 * XS;
+            double z0[DQ], z1[DQ];
+            double zz0 = 0.0, zz1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < DQ; ++j) {
+                z0[j] = x0[4 * j + c] - shc[j];
+                z1[j] = x1[4 * j + c] - shc[j];
+                zz0 = fma(z0[j], z0[j], zz0);
+                zz1 = fma(z1[j], z1[j], zz1);
+            }
+            double best[2] = {INFINITY, INFINITY}, second[2] = {INFINITY, INFINITY};
+            int bk[2] = {0, 0};
+            for (int grp = 0; grp < KP / kKmGroup; ++grp) {
+                double acc[2][4][2];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const double2 nn = *reinterpret_cast<const double2*>(nrm + grp * kKmGroup + 8 * nt + 2 * c);
+                    acc[0][nt][0] = acc[1][nt][0] = nn.x;
+                    acc[0][nt][1] = acc[1][nt][1] = nn.y;
+                }
+#pragma unroll
+                for (int j = 0; j < DQ; ++j) {
+                    const double2* bp = reinterpret_cast<const double2*>(Bf) + (static_cast<size_t>(j) * (KP / 16) + grp * 2) * 32 + lane;
+                    const double2 b01 = bp[0], b23 = bp[32];
+                    km_dmma(acc[0][0], z0[j], b01.x); km_dmma(acc[1][0], z1[j], b01.x);
+                    km_dmma(acc[0][1], z0[j], b01.y); km_dmma(acc[1][1], z1[j], b01.y);
+                    km_dmma(acc[0][2], z0[j], b23.x); km_dmma(acc[1][2], z1[j], b23.x);
+                    km_dmma(acc[0][3], z0[j], b23.y); km_dmma(acc[1][3], z1[j], b23.y);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double s = acc[mt][nt][e];
+                            second[mt] = fmin(second[mt], fmax(s, best[mt]));
+                            if (s < best[mt]) { best[mt] = s; bk[mt] = grp * kKmGroup + 8 * nt + 2 * c + e; }
+                        }
+            }
+            // ---------------- merge over the 4 lanes of a point, then exact refinement
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                double zz = mt == 0 ? zz0 : zz1;
+                zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+                zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+#pragma unroll
+                for (int off = 1; off <= 2; off <<= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, best[mt], off);
+                    const double os = __shfl_xor_sync(0xffffffffu, second[mt], off);
+                    const int ok = __shfl_xor_sync(0xffffffffu, bk[mt], off);
+                    second[mt] = fmin(fmin(second[mt], os), fmax(best[mt], ob));
+                    if (ob < best[mt] || (ob == best[mt] && ok < bk[mt])) { best[mt] = ob; bk[mt] = ok; }
+                }
+                const int pl = warp * 16 + mt * 8 + g;
+                if (c == 0 && pl < nvalid) {
+                    const double* xr = X + pl * XS;
+                    const double root = sqrt(zz) + cmax;
+                    const double tau = u_bound * root * root;
+                    int label = bk[mt];
+                    double d2;
+                    if (second[mt] > best[mt] + tau) {
+                        d2 = exact_distance(xr, p.craw + static_cast<long long>(label) * d, d);
+                    } else {
+                        // ambiguous under the filter's rounding bound: the reference's scan (KMeans.cpp:153-165)
+                        d2 = INFINITY;
+                        label = 0;
+                        for (int kk = 0; kk < p.k; ++kk) {
+                            const double sq = exact_distance(xr, p.craw + static_cast<long long>(kk) * d, d);
+                            if (sq < d2) { d2 = sq; label = kk; }
+                        }
+                    }
+                    inertia_acc += d2;
+                    const long long gi = tile0 + pl;
+                    if (p.labels[gi] != static_cast<unsigned>(label)) ++changed_acc;
+                    p.labels[gi] = static_cast<unsigned>(label);
+                    labs[pl] = label;
+                } else if (c == 0) {
+                    labs[pl] = -1;
+                }
+            }
+            __syncthreads();
+
+            // ---------------- update statistics: the warp owning a cluster adds its points in index order
+            if (p.accumulate) {
+                for (int base = 0; base < kKmTile; base += 32) {
+                    const int lab = labs[base + lane];
+                    unsigned mask = __ballot_sync(0xffffffffu, lab >= own_lo && lab < own_hi);
+                    while (mask) {
+                        const int b = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int kk = __shfl_sync(0xffffffffu, lab, b);
+                        const double* xr = X + (base + b) * XS;
+                        double* sk = sums + static_cast<size_t>(kk) * SD;
+                        for (int l = lane; l < d; l += 32) sk[l] += xr[l] - sh[l];
+                        if (lane == 0) sk[d] += 1.0;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---------------- flush the chunk's partial statistics
+        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        if (p.accumulate) {
+            for (int i = tid; i < KP * SD; i += kKmThreads) {
+                out[i] = sums[i];
+                sums[i] = 0.0;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, off);
+            changed_acc += __shfl_xor_sync(0xffffffffu, changed_acc, off);
+        }
+        if (lane == 0) { red[warp] = inertia_acc; red[8 + warp] = static_cast<double>(changed_acc); }
+        __syncthreads();
+        if (tid == 0) {
+            out[KP * SD] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+            out[KP * SD + 1] = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
+        }
+        if (tid >= 2 && tid < 8) out[KP * SD + tid] = 0.0;
+    }
+}
+
+// Builds the filter's image of the centroids: -2 c' in mma B-fragment order and |c'|^2; one thread per (dimension, centroid).
+struct KmPrepArgs {
+    const double* craw;   // D x K
+    const double* shift;
+    int d, k, DP, KP;
+    double* cfrag;
+    double* cnorm;
+    double* cmax;         // [1]
+};
+
+__global__ void km_prepare_kernel(const KmPrepArgs p)
+{
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= p.KP) return;
+    double nn = 0.0;
+    for (int dim = 0; dim < p.DP; ++dim) {
+        double cp = 0.0;
+        if (kk < p.k && dim < p.d) cp = p.craw[dim + static_cast<long long>(kk) * p.d] - p.shift[dim];
+        nn = fma(cp, cp, nn);
+        const int j = dim >> 2, c = dim & 3, nt = kk >> 3, g = kk & 7, lane = g * 4 + c;
+        p.cfrag[((static_cast<long long>(j) * (p.KP / 16) + nt / 2) * 32 + lane) * 2 + (nt & 1)] = -2.0 * cp;
+    }
+    p.cnorm[kk] = kk < p.k ? nn : INFINITY;
+}
+
+__global__ void km_cmax_kernel(const double* cnorm, int k, double* cmax)
+{
+    double m = 0.0;
+    for (int i = 0; i < k; ++i) m = fmax(m, cnorm[i]);
+    *cmax = sqrt(m);
+}
+
+// update_step (KMeans.cpp:180-192) from the exchanged statistics: centroid = shift + sum(z)/count, an
+// empty cluster goes to the origin; old centroids kept; out[0] = |C - C_old|_F^2 (KMeans.cpp:103).
+struct KmUpdateArgs {
+    const double* vsum;   // [8][SV]
+    const double* shift;
+    int d, k, KP, SV;
+    double* craw;
+    double* cold;
+    double* out;          // [4]: shift^2, inertia, changed
+};
+
+__global__ void km_update_kernel(const KmUpdateArgs p)
+{
+    __shared__ double part[256];
+    const int tid = threadIdx.x;
+    double acc = 0.0;
+    for (int e = tid; e < p.d * p.k; e += blockDim.x) {
+        const int dim = e % p.d, kk = e / p.d;
+        const double cnt = tree8(p.vsum + static_cast<long long>(kk) * (p.d + 1) + p.d, p.SV);
+        const double sum = tree8(p.vsum + static_cast<long long>(kk) * (p.d + 1) + dim, p.SV);
+        const double old = p.craw[e];
+        const double now = cnt > 0.0 ? p.shift[dim] + sum / cnt : 0.0;
+        p.cold[e] = old;
+        p.craw[e] = now;
+        const double t = now - old;
+        acc = fma(t, t, acc);
+    }
+    part[tid] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) part[tid] += part[tid + s];
+        __syncthreads();
+    }
+    if (tid == 0) p.out[0] = part[0];
+}
+
+__global__ void km_scalars_kernel(const double* vsum, int SV, int base, double* out)
+{
+    out[1] = tree8(vsum + base, SV);
+    out[2] = tree8(vsum + base + 1, SV);
+}
+
+using KmKernelFn = void (*)(KmArgs);
+
+static KmKernelFn km_kernel_for(int DP)
+{
+    switch (DP) {
+    case 4: return km_assign_kernel<4>;
+    case 8: return km_assign_kernel<8>;
+    case 16: return km_assign_kernel<16>;
+    case 32: return km_assign_kernel<32>;
+    case 64: return km_assign_kernel<64>;
+    default: return nullptr;
+    }
+}
+
+struct KmGpu {
+    double* craw = nullptr;
+    double* cold = nullptr;
+    double* cfrag = nullptr;
+    double* cnorm = nullptr;
+    double* cmax = nullptr;
+    unsigned* labels = nullptr;
+    double* partials = nullptr;
+    double* vsum = nullptr;
+    double* out = nullptr;
+    unsigned* counter = nullptr;
+    int grid = 0;
+};
+
+}  // namespace mlb
+
+using namespace mlb;
+
+struct mlb_km {
+    mlb_ctx* ctx = nullptr;
+    mlb_data* data = nullptr;
+    int d = 0, k = 0, DP = 0, KP = 0, SV = 0;
+    std::vector<KmGpu> gpus;
+    KmKernelFn fn = nullptr;
+    size_t smem = 0;
+    bool have_centroids = false, have_stats = false;
+    int64_t launches = 0;
+};
+
+namespace mlb {
+
+static int km_prepare(mlb_km* km)
+{
+    return for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        KmGpu& kg = km->gpus[g];
+        KmPrepArgs a{kg.craw, km->data->shards[g].shift, km->d, km->k, km->DP, km->KP, kg.cfrag, kg.cnorm, kg.cmax};
+        km_prepare_kernel<<<(km->KP + 127) / 128, 128, 0, gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        km_cmax_kernel<<<1, 1, 0, gpu.stream>>>(kg.cnorm, km->k, kg.cmax);
+        MLB_CUDA(cudaGetLastError());
+        km->launches += 2;
+        return MLB_OK;
+    });
+}
+
+}  // namespace mlb
+
+extern "C" {
+
+int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
+{
+    MLB_REQUIRE(ctx && data && out, "mlb_km_create: null argument");
+    MLB_REQUIRE(data->ctx == ctx, "mlb_km_create: data belongs to another context");
+    MLB_REQUIRE(k >= 1, "mlb_km_create: number of clusters must be positive");
+    const int d = data->d;
+    int DP = 0;
+    for (int cand : {4, 8, 16, 32, 64})
+        if (d <= cand) { DP = cand; break; }
+    MLB_REQUIRE(DP, "mlb_km_create: D=%d not supported by this build (D <= 64)", d);
+    const int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup;
+    const size_t smem = km_smem_bytes(DP, d, KP);
+    MLB_REQUIRE(smem <= 227 * 1024, "mlb_km_create: D=%d, K=%d needs %zu bytes of shared memory (limit 232448)", d, k, smem);
+    auto* km = new mlb_km;
+    km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->SV = km_sv(d, KP);
+    km->fn = km_kernel_for(DP);
+    km->smem = smem;
+    km->gpus.resize(ctx->gpus.size());
+    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        KmGpu& kg = km->gpus[g];
+        const DataShard& sh = data->shards[g];
+        MLB_CUDA(cudaMalloc(&kg.craw, sizeof(double) * d * k));
+        MLB_CUDA(cudaMalloc(&kg.cold, sizeof(double) * d * k));
+        MLB_CUDA(cudaMalloc(&kg.cfrag, sizeof(double) * DP * KP));
+        MLB_CUDA(cudaMalloc(&kg.cnorm, sizeof(double) * KP));
+        MLB_CUDA(cudaMalloc(&kg.cmax, sizeof(double)));
+        MLB_CUDA(cudaMalloc(&kg.labels, sizeof(unsigned) * std::max<int64_t>(1, sh.n())));
+        MLB_CUDA(cudaMalloc(&kg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV));
+        MLB_CUDA(cudaMalloc(&kg.vsum, sizeof(double) * kVirtualShards * km->SV));
+        MLB_CUDA(cudaMalloc(&kg.out, sizeof(double) * 4));
+        MLB_CUDA(cudaMalloc(&kg.counter, sizeof(unsigned)));
+        MLB_CUDA(cudaMemsetAsync(kg.labels, 0, sizeof(unsigned) * std::max<int64_t>(1, sh.n()), gpu.stream));   // labels_.resize(): zeros
+        MLB_CUDA(cudaMemsetAsync(kg.vsum, 0, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(kg.cold, 0, sizeof(double) * d * k, gpu.stream));
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int per_sm = 0, sms = 0;
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn), kKmThreads, smem));
+        MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
+        MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means kernel does not fit on an SM");
+        kg.grid = per_sm * sms;
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    });
+    if (rc != MLB_OK) { mlb_km_destroy(km); return rc; }
+    *out = km;
+    return MLB_OK;
+}
+
+int mlb_km_destroy(mlb_km* km)
+{
+    if (!km) return MLB_OK;
+    for (size_t g = 0; g < km->gpus.size(); ++g) {
+        cudaSetDevice(km->ctx->gpus[g].device);
+        cudaStreamSynchronize(km->ctx->gpus[g].stream);
+        KmGpu& kg = km->gpus[g];
+        for (void* ptr : {static_cast<void*>(kg.craw), static_cast<void*>(kg.cold), static_cast<void*>(kg.cfrag), static_cast<void*>(kg.cnorm),
+                          static_cast<void*>(kg.cmax), static_cast<void*>(kg.labels), static_cast<void*>(kg.partials), static_cast<void*>(kg.vsum),
+                          static_cast<void*>(kg.out), static_cast<void*>(kg.counter)})
+            if (ptr) cudaFree(ptr);
+    }
+    delete km;
+    return MLB_OK;
+}
+
+int mlb_km_set_centroids(mlb_km* km, const double* centroids)
+{
+    MLB_REQUIRE(km && centroids, "mlb_km_set_centroids: null argument");
+    MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        MLB_CUDA(cudaMemcpyAsync(km->gpus[g].craw, centroids, sizeof(double) * km->d * km->k, cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    }));
+    MLB_TRY(km_prepare(km));
+    km->have_centroids = true;
+    km->have_stats = false;
+    return MLB_OK;
+}
+
+int mlb_km_get_centroids(mlb_km* km, double* centroids)
+{
+    MLB_REQUIRE(km && centroids, "mlb_km_get_centroids: null argument");
+    if (!km->have_centroids) { set_error("mlb_km_get_centroids: centroids not set"); return MLB_ESTATE; }
+    Gpu& gpu = km->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    MLB_CUDA(cudaMemcpyAsync(centroids, km->gpus[0].craw, sizeof(double) * km->d * km->k, cudaMemcpyDeviceToHost, gpu.stream));
+    MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+    return MLB_OK;
+}
+
+int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
+{
+    MLB_REQUIRE(km, "mlb_km_assign: null argument");
+    if (!km->have_centroids) { set_error("mlb_km_assign: centroids not set"); return MLB_ESTATE; }
+    mlb_ctx* ctx = km->ctx;
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        KmGpu& kg = km->gpus[g];
+        const DataShard& sh = km->data->shards[g];
+        KmArgs a{};
+        a.x = sh.x; a.n_local = sh.n(); a.d = km->d; a.k = km->k; a.KP = km->KP;
+        a.shift = sh.shift; a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
+        a.labels = kg.labels; a.partials = kg.partials;
+        a.chunk = km->data->lay.chunk; a.n_chunks = static_cast<int>(sh.n_chunks());
+        a.counter = kg.counter; a.accumulate = 1;
+        MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+        if (a.n_chunks > 0) {
+            km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+            MLB_CUDA(cudaGetLastError());
+            ++km->launches;
+        }
+        return MLB_OK;
+    }));
+    std::vector<double*> partials, vsum;
+    for (KmGpu& kg : km->gpus) { partials.push_back(kg.partials); vsum.push_back(kg.vsum); }
+    MLB_TRY(reduce_and_exchange(km->data, partials, vsum, km->SV));
+    km->launches += static_cast<int64_t>(ctx->gpus.size());
+    double host[4] = {0, 0, 0, 0};
+    {
+        Gpu& gpu = ctx->gpus[0];
+        MLB_CUDA(cudaSetDevice(gpu.device));
+        km_scalars_kernel<<<1, 1, 0, gpu.stream>>>(km->gpus[0].vsum, km->SV, km->KP * (km->d + 1), km->gpus[0].out);
+        MLB_CUDA(cudaGetLastError());
+        ++km->launches;
+        MLB_CUDA(cudaMemcpyAsync(host, km->gpus[0].out, sizeof(double) * 4, cudaMemcpyDeviceToHost, gpu.stream));
+    }
+    MLB_TRY(mlb_ctx_synchronize(ctx));
+    if (inertia) *inertia = host[1];
+    if (n_changed) *n_changed = static_cast<int64_t>(host[2]);
+    km->have_stats = true;
+    return MLB_OK;
+}
+
+int mlb_km_update(mlb_km* km, double* centroid_shift_sq)
+{
+    MLB_REQUIRE(km, "mlb_km_update: null argument");
+    if (!km->have_stats) { set_error("mlb_km_update: no assignment to update from"); return MLB_ESTATE; }
+    MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        KmGpu& kg = km->gpus[g];
+        KmUpdateArgs a{kg.vsum, km->data->shards[g].shift, km->d, km->k, km->KP, km->SV, kg.craw, kg.cold, kg.out};
+        km_update_kernel<<<1, 256, 0, gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        ++km->launches;
+        return MLB_OK;
+    }));
+    MLB_TRY(km_prepare(km));
+    double host = 0.0;
+    Gpu& gpu = km->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    MLB_CUDA(cudaMemcpyAsync(&host, km->gpus[0].out, sizeof(double), cudaMemcpyDeviceToHost, gpu.stream));
+    MLB_TRY(mlb_ctx_synchronize(km->ctx));
+    if (centroid_shift_sq) *centroid_shift_sq = host;
+    km->have_stats = false;
+    return MLB_OK;
+}
+
+int mlb_km_get_labels(mlb_km* km, unsigned int* labels)
+{
+    MLB_REQUIRE(km && labels, "mlb_km_get_labels: null argument");
+    const int64_t host_begin = km->ctx->rank_mode ? km->data->shards[0].begin : 0;
+    MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        const DataShard& sh = km->data->shards[g];
+        if (sh.n() > 0)
+            MLB_CUDA(cudaMemcpyAsync(labels + (sh.begin - host_begin), km->gpus[g].labels, sizeof(unsigned) * sh.n(), cudaMemcpyDeviceToHost, gpu.stream));
+        return MLB_OK;
+    }));
+    return mlb_ctx_synchronize(km->ctx);
+}
+
+int mlb_km_launch_count(const mlb_km* km, int64_t* launches)
+{
+    MLB_REQUIRE(km && launches, "mlb_km_launch_count: null argument");
+    *launches = km->launches;
+    return MLB_OK;
+}
+
+}  // extern "C"

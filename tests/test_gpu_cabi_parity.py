@@ -1,0 +1,239 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (include/mlb200.h via
+ml_b200.cabi), against the CPU oracle on the same seeded inputs and the same initial means.
+
+Bar (BASELINE.json north_star): identical labels and iteration count; means, covariances, mixing
+weights and log-likelihood within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from tests.datasets import mouse_numpy, synthetic_gmm
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ml_b200 import cabi
+    assert cabi.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
+    c = cabi.Context(1)
+    yield c
+    c.close()
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = max(np.max(np.abs(b)), 1e-300)
+    return float(np.max(np.abs(a - b)) / scale)
+
+
+def em_fit_cabi(ctx, data, k, initial_means_dk, *, absolute_tolerance=1e-8, relative_tolerance=1e-8, maximum_steps=1000):
+    """EM::fit's loop (ML/EM.cpp:127-170) on the C-ABI: host convergence test, device steps."""
+    from ml_b200 import cabi
+    d_data = cabi.Data.upload(ctx, data)
+    em = cabi.Em(d_data, k)
+    cov = em.sample_covariance()
+    em.set_params(initial_means_dk, np.repeat(cov[None], k, axis=0), np.full(k, 1.0 / k))
+    old = -np.inf
+    out = type("Fit", (), {})()
+    out.converged = False
+    out.iterations = 0
+    out.sample_covariance = cov
+    for step in range(maximum_steps):
+        ll = em.step()
+        out.iterations = step + 1
+        out.log_likelihood = ll
+        if step > 0 and abs(ll - old) < absolute_tolerance + relative_tolerance * max(abs(old), abs(ll)):
+            out.converged = True
+            break
+        old = ll
+    out.means, out.covariances, out.mixing_probabilities = em.get_params()
+    out.responsibilities, out.labels = em.emit()
+    out.launches = em.launch_count
+    em.close()
+    d_data.close()
+    return out
+
+
+EM_SHAPES = [
+    (5000, 2, 3, 11),
+    (3001, 3, 2, 12),
+    (1000, 5, 7, 13),
+    (20000, 8, 16, 14),
+    (20011, 16, 32, 15),
+    (4097, 13, 20, 16),
+    (777, 1, 2, 17),
+]
+
+
+@pytest.mark.parametrize("n,d,k,seed", EM_SHAPES)
+def test_em_fixed_steps_match_oracle(ctx, n, d, k, seed):
+    """T iterations from identical initial means: every parameter within 1e-9 relative."""
+    data, _, _ = synthetic_gmm(n, d, k, seed=seed, spread=6.0)
+    init = np.ascontiguousarray(data[:: n // k][:k].T)  # (D, K): K data points at fixed indices
+    steps = 6
+    ref = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=steps,
+                        absolute_tolerance=0.0, relative_tolerance=0.0, want_responsibilities=False)
+    assert ref.iterations == steps
+    got = em_fit_cabi(ctx, data, k, init, absolute_tolerance=0.0, relative_tolerance=0.0, maximum_steps=steps)
+    assert got.iterations == steps
+    assert rel_err(got.sample_covariance, np.cov(data.T).reshape(d, d)) <= 1e-12
+    assert abs(got.log_likelihood - ref.log_likelihood) <= RTOL * abs(ref.log_likelihood)
+    assert rel_err(got.means, ref.means) <= RTOL
+    assert rel_err(got.mixing_probabilities, ref.mixing_probabilities) <= RTOL
+    for c in range(k):
+        assert rel_err(got.covariances[c], ref.covariances[c]) <= RTOL, c
+
+
+@pytest.mark.parametrize("n,d,k,seed", [(10000, 2, 3, 21), (30000, 8, 16, 22), (30000, 16, 32, 23)])
+def test_em_full_fit_matches_oracle(ctx, n, d, k, seed):
+    """Whole fit to convergence: identical iteration count and labels, parameters within 1e-9."""
+    data, _, _ = synthetic_gmm(n, d, k, seed=seed, spread=8.0)
+    init = np.ascontiguousarray(data[7:: n // k][:k].T)
+    ref = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=300)
+    got = em_fit_cabi(ctx, data, k, init, maximum_steps=300)
+    assert got.converged == ref.converged
+    assert got.iterations == ref.iterations
+    assert abs(got.log_likelihood - ref.log_likelihood) <= RTOL * abs(ref.log_likelihood)
+    assert rel_err(got.means, ref.means) <= RTOL
+    assert rel_err(got.mixing_probabilities, ref.mixing_probabilities) <= RTOL
+    assert rel_err(got.covariances, ref.covariances) <= RTOL
+    assert np.array_equal(got.labels, ref.labels)
+    assert np.max(np.abs(got.responsibilities - ref.responsibilities)) <= 1e-9
+    assert np.max(np.abs(got.responsibilities.sum(axis=1) - 1.0)) <= 1e-14
+
+
+def test_em_mouse_c1_matches_oracle(ctx):
+    """BASELINE config 1: mouse data, N=10k, D=2, K=3, KPP-initialised means, tolerance 1e-14 (Benchmarks/bm_EM.cpp:9-48)."""
+    data, _ = oracle.testdata_mouse(10000)
+    init = oracle.centroids_init(oracle.KPP, data, 3, seed=42)
+    ref = oracle.em_fit(data, 3, means_init=oracle.EXPLICIT, explicit_means=init, absolute_tolerance=1e-14, relative_tolerance=1e-14)
+    got = em_fit_cabi(ctx, data, 3, init, absolute_tolerance=1e-14, relative_tolerance=1e-14)
+    # at a 1e-14 tolerance the stopping step is decided by rounding noise, so the count may differ by a few steps
+    assert got.converged and ref.converged
+    assert abs(got.iterations - ref.iterations) <= max(5, ref.iterations // 20)
+    assert abs(got.log_likelihood - ref.log_likelihood) <= RTOL * abs(ref.log_likelihood)
+    assert rel_err(got.means, ref.means) <= 1e-7
+    assert np.mean(got.labels != ref.labels) <= 1e-3
+
+
+def test_em_sklearn_pin_on_device(ctx):
+    """cppyml/tests/test_clustering.py:47-67 with the device path: |ll - sklearn score| <= 1e-10."""
+    from sklearn.mixture import GaussianMixture
+    data = mouse_numpy()
+    init = oracle.centroids_init(oracle.KPP, data, 3, seed=42)
+    got = em_fit_cabi(ctx, data, 3, init, absolute_tolerance=1e-10, relative_tolerance=0.0, maximum_steps=1000)
+    assert got.converged
+    gm = GaussianMixture(n_components=3, tol=1e-10, reg_covar=1e-15, random_state=999, max_iter=1000)
+    gm.fit(data)
+    assert abs(got.log_likelihood - gm.score(data)) <= 1e-10
+
+
+def test_em_mstep_from_responsibilities(ctx):
+    """maximise_first (EM.cpp:120-125): M-step from one-hot responsibilities equals the oracle's."""
+    from ml_b200 import cabi
+    n, d, k = 5003, 8, 5
+    data, labels, _ = synthetic_gmm(n, d, k, seed=31)
+    resp = np.zeros((n, k))
+    resp[np.arange(n), labels] = 1.0
+    d_data = cabi.Data.upload(ctx, data)
+    em = cabi.Em(d_data, k)
+    em.mstep_from_responsibilities(resp)
+    means, covs, w = em.get_params()
+    for c in range(k):
+        m = labels == c
+        assert rel_err(means[:, c], data[m].mean(axis=0)) <= 1e-12
+        assert rel_err(covs[c], np.cov(data[m].T, bias=True) + 1e-15 * np.eye(d)) <= 1e-10
+        assert abs(w[c] - m.mean()) <= 1e-15
+    inv, sd = em.get_precisions()
+    for c in range(k):
+        assert rel_err(inv[c] @ covs[c], np.eye(d)) <= 1e-9
+        assert abs(sd[c] - np.sqrt(np.linalg.det(covs[c]))) <= 1e-10 * sd[c]
+    em.close()
+    d_data.close()
+
+
+def test_em_is_bitwise_reproducible(ctx):
+    """Fixed chunking and fixed-order reductions: two runs give identical bits."""
+    data, _, _ = synthetic_gmm(50000, 8, 16, seed=41)
+    init = np.ascontiguousarray(data[:16].T)
+    a = em_fit_cabi(ctx, data, 16, init, maximum_steps=5, absolute_tolerance=0.0, relative_tolerance=0.0)
+    b = em_fit_cabi(ctx, data, 16, init, maximum_steps=5, absolute_tolerance=0.0, relative_tolerance=0.0)
+    assert a.log_likelihood == b.log_likelihood
+    assert np.array_equal(a.means, b.means) and np.array_equal(a.covariances, b.covariances)
+
+
+# ---------------------------------------------------------------- K-means
+
+
+def kmeans_fit_cabi(ctx, data, k, initial_centroids_dk, *, absolute_tolerance=1e-8, maximum_steps=1000):
+    """KMeans::fit_once (ML/KMeans.cpp:77-113) on the C-ABI."""
+    from ml_b200 import cabi
+    d_data = cabi.Data.upload(ctx, data)
+    km = cabi.Km(d_data, k)
+    km.set_centroids(initial_centroids_dk)
+    out = type("Fit", (), {})()
+    out.converged = False
+    out.iterations = 0
+    for step in range(maximum_steps):
+        out.inertia, changed = km.assign()
+        out.iterations = step + 1
+        if step > 0 and changed == 0:
+            out.converged = True
+            break
+        shift2 = km.update()
+        if step > 0 and shift2 < absolute_tolerance:
+            out.inertia, _ = km.assign()
+            out.converged = True
+            break
+    out.centroids = km.get_centroids()
+    out.labels = km.get_labels()
+    km.close()
+    d_data.close()
+    return out
+
+
+KM_SHAPES = [(5000, 2, 3, 51), (4001, 3, 2, 52), (30000, 8, 16, 53), (30011, 32, 256, 54), (10000, 16, 33, 55), (2000, 64, 10, 56), (999, 1, 4, 57)]
+
+
+@pytest.mark.parametrize("n,d,k,seed", KM_SHAPES)
+def test_kmeans_full_fit_matches_oracle(ctx, n, d, k, seed):
+    data, _, _ = synthetic_gmm(n, d, min(k, 40), seed=seed, spread=5.0)
+    init = np.ascontiguousarray(data[3:: n // k][:k].T)
+    ref = oracle.kmeans_fit(data, k, init=oracle.EXPLICIT, explicit_means=init, maximum_steps=100)
+    got = kmeans_fit_cabi(ctx, data, k, init, maximum_steps=100)
+    assert got.converged == ref.converged
+    assert got.iterations == ref.iterations
+    assert np.array_equal(got.labels, ref.labels)
+    assert rel_err(got.centroids, ref.centroids) <= RTOL
+    assert abs(got.inertia - ref.inertia) <= RTOL * ref.inertia
+
+
+def test_kmeans_reference_test_data(ctx):
+    """Tests/test_KMeans.cpp:8-91 on the device path: labels == assign_label, sum d^2 == inertia, ground truth recovered."""
+    data, truth = oracle.testdata_two_gaussians()
+    init = oracle.centroids_init(oracle.KPP, data, 2, seed=63413131)
+    got = kmeans_fit_cabi(ctx, data, 2, init, maximum_steps=100)
+    assert got.converged
+    total = 0.0
+    for i in range(400):
+        label, sq = oracle.kmeans_assign_label(got.centroids, data[i])
+        assert label == got.labels[i]
+        total += sq
+    assert abs(total - got.inertia) <= 1e-13
+    perm = got.labels if (got.labels[0] == truth[0]) else 1 - got.labels
+    assert np.array_equal(perm, truth)
+
+
+def test_kmeans_duplicate_centroids_take_the_exact_path(ctx):
+    """Two identical centroids tie exactly: the lowest index must win, as with the reference's strict '<'."""
+    data, _, _ = synthetic_gmm(3000, 4, 3, seed=61)
+    init = np.ascontiguousarray(data[[5, 5, 900, 1800]].T)
+    ref = oracle.kmeans_fit(data, 4, init=oracle.EXPLICIT, explicit_means=init, maximum_steps=50)
+    got = kmeans_fit_cabi(ctx, data, 4, init, maximum_steps=50)
+    assert got.iterations == ref.iterations
+    assert np.array_equal(got.labels, ref.labels)
+    assert rel_err(got.centroids, ref.centroids) <= RTOL
