@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the clustering hot path (BASELINE.json): Gaussian-mixture EM iterations.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --steps K --warmup W     # the reference algorithm on the host CPU
+
+A "step" is one EM iteration (E-step + M-step + statistics exchange + parameter refresh) over the whole
+synthetic data set.  Workload at 1 GPU: BASELINE config 2, full-covariance GMM, N=10M, D=8, K=16; with
+--gpus G every rank holds N=10M points (weak scaling, one process per GPU, launched by torchrun).
+`--workload c3` selects N=100M/8 per GPU... see WORKLOADS.  metric = point-component pairs per second.
+
+One JSON line on stdout (rank 0).  `value` is timed with CUDA events on the library's stream with the data
+resident in HBM; `e2e` is the same metric for a whole fit through the C-ABI from HOST (pinned) buffers,
+upload and result download inside the timed region; `roofline` is the fused kernel against the measured
+FP64 pipe peak; `cpu_baseline` is the CPU oracle (a port of the reference's single-threaded loops) on a
+bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name -> (points per GPU, D, K).  Per-GPU sizes so that --gpus 8 on c3 is the north star's N=100M, D=16, K=32.
+WORKLOADS = {
+    "c2": (10_000_000, 8, 16),
+    "c3": (12_500_000, 16, 32),
+}
+METRIC = "em_point_components_per_second"
+UNIT = "Gpoint*comp/s"
+DATA_SEED = 20261018
+# FP64 peak of this pool's B200s measured with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json): a chain of
+# mma.sync.m8n8k4.f64 (DMMA), the instruction the kernels issue; DFMA measured 36.5.  MEASURED_PEAKS.json has
+# no FP64 figure, so this is the denominator, re-measured live below when the tool binary is present.
+FP64_PEAK_TFLOPS_MEASURED = 37.0
+
+
+def f_em(d):
+    """Algorithmic FP64 flops per point-component pair per iteration."""
+    return 2 * d * d + 8 * d + 6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU sample (0 = default)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(n_cpu, d, k, steps, warmup):
+    """The CPU oracle (oracle/mlpp_oracle.cpp: the reference's single-threaded loops restated) on a bounded
+    sample of the same synthetic mixture; per-iteration times come from the oracle's own clock."""
+    import numpy as np
+    import oracle
+    from tests.datasets import synthetic_gmm
+    data, _, _ = synthetic_gmm(n_cpu, d, k, seed=DATA_SEED % 1000, spread=10.0)
+    init = np.ascontiguousarray(data[:k].T)
+    fit = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=warmup + steps,
+                        absolute_tolerance=0.0, relative_tolerance=0.0, want_responsibilities=True)
+    secs = fit.step_seconds[warmup:]
+    mean = float(np.mean(secs))
+    return {"value": n_cpu * k / mean / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle em_fit, N={n_cpu} D={d} K={k}, {len(secs)} timed iterations after {warmup} warm-up, single thread like the reference",
+            "ms_per_step": mean * 1e3, "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host CPU.  The reference binary cannot be built in
+    this image (Eigen 3 absent), so this is the oracle port; ml::EM is single-threaded, so is this."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpu, d, k = WORKLOADS[args.workload]
+    n_cpu = args.cpu_sample or 200_000
+    base = cpu_baseline(n_cpu, d, k, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: ml::EM full-covariance GMM, D={d}, K={k}; CPU sample of N={n_cpu} points (throughput is per point, O(N) per iteration)",
+                   "points": n_cpu, "dims": d, "components": k},
+        "cpu_baseline": {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ml_b200 import cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [cabi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n_per_gpu, d, k = WORKLOADS[args.workload]
+    n_total = n_per_gpu * world
+    ctx = cabi.Context.for_rank(local_rank, rank, world, uid)
+    data = cabi.Data.generate_gmm(ctx, n_total, d, k, seed=DATA_SEED)
+    _, n_local, _ = data.shape
+
+    # Initial means: K data points at fixed global indices (0..K-1, held by rank 0), identical on every rank.
+    box = [data.download(0, k) if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    init_means = np.ascontiguousarray(box[0].T)
+
+    em = cabi.Em(data, k)
+    cov = em.sample_covariance()
+    em.set_params(init_means, np.repeat(cov[None], k, axis=0), np.full(k, 1.0 / k))
+
+    # ---- value: K steps with the data resident in HBM, CUDA events on the library's stream, max over ranks
+    em.run_steps(args.warmup, want_ll=False)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = em.launch_count
+    em.set_kernel_timing(True)
+    barrier()
+    ctx.timer_start()
+    lls = em.run_steps(args.steps, want_ll=True)
+    ms_total = ctx.timer_stop()
+    barrier()
+    kernel_ms, kernel_launches = em.kernel_time_ms()
+    em.set_kernel_timing(False)
+    launches = em.launch_count - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ms_total)
+    ms_per_step = ms_total / args.steps
+    value = n_total * k / (ms_per_step * 1e-3) / 1e9
+    kernel_ms_avg = max_over_ranks(kernel_ms / max(1, kernel_launches))
+
+    # ---- e2e: a whole fit through the C-ABI from pinned host memory (upload, init, K iterations with the
+    # log-likelihood read back every iteration, parameters and labels downloaded), wall clock, max over ranks
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n_local, d), dtype=torch.float64, pin_memory=True)
+        begin, _ = cabi.shard_range(n_total, world, rank)
+        host_np = host.numpy()
+        host_np[:] = data.download(begin, n_local)
+        em.close(); data.close()
+        em = data = None
+
+        def one_fit():
+            barrier()
+            t0 = time.perf_counter()
+            d2 = cabi.Data.upload(ctx, host_np, n_total=n_total)
+            e2 = cabi.Em(d2, k)
+            c2 = e2.sample_covariance()
+            e2.set_params(init_means, np.repeat(c2[None], k, axis=0), np.full(k, 1.0 / k))
+            ll = 0.0
+            for _ in range(args.steps):
+                ll = e2.step()
+            params = e2.get_params()
+            _, labels = e2.emit(want_responsibilities=False, want_labels=True)
+            ctx.synchronize()
+            barrier()
+            dt = time.perf_counter() - t0
+            e2.close(); d2.close()
+            return dt, ll, params, labels
+
+        one_fit()  # warm-up (allocator, page faults of the staging paths)
+        dt, ll_e2e, _, labels = one_fit()
+        dt = max_over_ranks(dt)
+        h2d = n_local * d * 8 + (d * k + k * d * d + k) * 8
+        d2h = n_local * 4 + (d * k + k * d * d + k) * 8 + args.steps * 8 + d * d * 8
+        e2e = {"value": n_total * k * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+               "fit_seconds": dt, "iterations": args.steps,
+               "what": "one whole fit through the C-ABI from pinned host memory: upload of the rank's points, sample covariance, set_params, "
+                       f"{args.steps} iterations each reading back the log-likelihood, parameters and N labels downloaded; bytes are per iteration (totals / iterations)",
+               "log_likelihood": ll_e2e}
+        assert abs(ll_e2e - float(lls[-1])) <= 1e-12 * abs(ll_e2e), "the e2e fit and the resident run disagree"
+
+    if rank == 0:
+        flops_per_launch = n_per_gpu * k * f_em(d)
+        achieved = flops_per_launch / (kernel_ms_avg * 1e-3) / 1e12
+        peak = FP64_PEAK_TFLOPS_MEASURED
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: ml::EM full-covariance GMM, N={n_per_gpu} per GPU ({n_total} total), D={d}, K={k}, "
+                                   "initial means = data points 0..K-1, initial covariances = sample covariance",
+                       "points_total": n_total, "points_per_gpu": n_per_gpu, "dims": d, "components": k,
+                       "parallelism": f"points sharded over {world} GPU(s), one ncclAllGather of the sufficient statistics per iteration",
+                       "l2": f"input is {n_per_gpu * d * 8 / 1e6:.0f} MB per GPU, larger than the 126 MB L2; no flush needed between iterations",
+                       "iterations_per_second": 1e3 / ms_per_step},
+            "roofline": {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64); shares the SM's FP64 unit with DFMA",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": "measured on this pool with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json has no FP64 figure",
+                         "kernel": "em_kernel<DP,KP,0> (fused E+M)", "kernel_ms_avg": kernel_ms_avg, "kernel_launches_timed": kernel_launches,
+                         "flops_per_launch": flops_per_launch, "flops_per_point_component": f_em(d),
+                         "hbm_achieved_gbs": n_per_gpu * d * 8 / (kernel_ms_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                         "hbm_frac": n_per_gpu * d * 8 / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
+                         "traffic": None},
+            "clocks": clock_info,
+            "gpu_launches": launches,
+            "log_likelihood_last": float(lls[-1]),
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(prof):
+            line["roofline"]["traffic"] = json.load(open(prof)).get(args.workload)
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            n_cpu = args.cpu_sample or 500_000
+            line["cpu_baseline"] = cpu_baseline(n_cpu, d, k, 3, 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

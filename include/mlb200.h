@@ -148,6 +148,17 @@ int mlb_em_get_precisions(mlb_em* em, double* inverse_covariances, double* sqrt_
  * Rank contexts receive their own rows. */
 int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_out);
 
+/* The same for the GLOBAL point range [begin, begin + count) only (resp_out is count x K with leading
+ * dimension ld, labels_out has count entries).  Rank contexts can only emit rows they hold. */
+int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out, int64_t ld, unsigned int* labels_out);
+
+/* Per-launch device timing of the dominant kernel (the fused E+M kernel) for roofline reports:
+ * CUDA events recorded on the launching stream around each launch while enabled (at most 4096
+ * launches are kept).  mlb_em_kernel_time_ms synchronises and returns the summed duration and the
+ * number of launches measured on the first local GPU. */
+int mlb_em_set_kernel_timing(mlb_em* em, int enabled);
+int mlb_em_kernel_time_ms(mlb_em* em, double* total_ms, int64_t* launches);
+
 /* Which device path the last step used: 1 = fused DMMA E+M kernel, 2 = split E / M kernels. */
 int mlb_em_last_path(const mlb_em* em, int* path);
 /* Number of kernels the library launched on this object since creation (bench "gpu_launches"). */
@@ -176,6 +187,9 @@ int mlb_km_update(mlb_km* km, double* centroid_shift_sq);
 /* labels_ of the last assignment; rank contexts receive their own range. */
 int mlb_km_get_labels(mlb_km* km, unsigned int* labels);
 int mlb_km_launch_count(const mlb_km* km, int64_t* launches);
+/* As mlb_em_set_kernel_timing / mlb_em_kernel_time_ms, for the assignment kernel. */
+int mlb_km_set_kernel_timing(mlb_km* km, int enabled);
+int mlb_km_kernel_time_ms(mlb_km* km, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,9 @@ SIGNATURES = {
     "mlb_em_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "mlb_em_get_precisions": (ctypes.c_int, [_vp, _vp, _vp]),
     "mlb_em_emit": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
+    "mlb_em_emit_range": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int64, _vp]),
+    "mlb_em_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "mlb_em_kernel_time_ms": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
     "mlb_em_last_path": (ctypes.c_int, [_vp, _c_ip]),
     "mlb_em_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
     "mlb_km_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
@@ -65,6 +68,8 @@ SIGNATURES = {
     "mlb_km_update": (ctypes.c_int, [_vp, _c_dp]),
     "mlb_km_get_labels": (ctypes.c_int, [_vp, _vp]),
     "mlb_km_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
+    "mlb_km_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "mlb_km_kernel_time_ms": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
 }
 
 _lib = None
@@ -284,6 +289,15 @@ class Em:
         check(lib().mlb_em_emit(self._h, _ptr(resp), n, _ptr(labels)))
         return resp, labels
 
+    def set_kernel_timing(self, enabled):
+        check(lib().mlb_em_set_kernel_timing(self._h, int(enabled)))
+
+    def kernel_time_ms(self):
+        """(summed duration in ms, launches) of the fused kernel since timing was enabled."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        check(lib().mlb_em_kernel_time_ms(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
     @property
     def last_path(self):
         p = ctypes.c_int()
@@ -342,6 +356,14 @@ class Km:
         labels = np.empty(self.n_local, dtype=np.uint32)
         check(lib().mlb_km_get_labels(self._h, _ptr(labels)))
         return labels
+
+    def set_kernel_timing(self, enabled):
+        check(lib().mlb_km_set_kernel_timing(self._h, int(enabled)))
+
+    def kernel_time_ms(self):
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        check(lib().mlb_km_kernel_time_ms(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     @property
     def launch_count(self):

@@ -21,6 +21,48 @@ void set_error(const char* fmt, ...)
     g_last_error = buf;
 }
 
+int KernelTimer::begin(cudaStream_t stream)
+{
+    if (!enabled || used / 2 >= kMaxLaunches) return MLB_OK;
+    if (events.size() < used + 2) {
+        events.resize(used + 2, nullptr);
+        MLB_CUDA(cudaEventCreate(&events[used]));
+        MLB_CUDA(cudaEventCreate(&events[used + 1]));
+    }
+    MLB_CUDA(cudaEventRecord(events[used], stream));
+    return MLB_OK;
+}
+
+int KernelTimer::end(cudaStream_t stream)
+{
+    if (!enabled || used / 2 >= kMaxLaunches) return MLB_OK;
+    MLB_CUDA(cudaEventRecord(events[used + 1], stream));
+    used += 2;
+    return MLB_OK;
+}
+
+int KernelTimer::total(double* total_ms, int64_t* launches)
+{
+    double sum = 0;
+    for (size_t i = 0; i + 1 < used; i += 2) {
+        MLB_CUDA(cudaEventSynchronize(events[i + 1]));
+        float ms = 0;
+        MLB_CUDA(cudaEventElapsedTime(&ms, events[i], events[i + 1]));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = static_cast<int64_t>(used / 2);
+    return MLB_OK;
+}
+
+void KernelTimer::destroy()
+{
+    for (cudaEvent_t e : events)
+        if (e) cudaEventDestroy(e);
+    events.clear();
+    used = 0;
+}
+
 Layout Layout::make(int64_t n_total)
 {
     Layout lay;

@@ -505,6 +505,7 @@ struct EmGpu {
     double* stage = nullptr;   // emit / responsibilities staging
     unsigned* stage_labels = nullptr;
     int grid = 0;
+    KernelTimer timer;
 };
 
 constexpr int kLlRing = 4096;
@@ -568,8 +569,11 @@ static int launch_em(mlb_em* em, EmKernelFn fn, const EmArgs& a, int g, int grid
     Gpu& gpu = em->ctx->gpus[g];
     MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
     if (a.n_chunks > 0) {
+        const bool timed = fn == em->fn_step;
+        if (timed) MLB_TRY(em->gpus[g].timer.begin(gpu.stream));
         fn<<<std::min(grid, a.n_chunks), kEmThreads, em_smem_bytes(em->DP, em->KP), gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
+        if (timed) MLB_TRY(em->gpus[g].timer.end(gpu.stream));
         ++em->launches;
     }
     return MLB_OK;
@@ -698,6 +702,7 @@ int mlb_em_destroy(mlb_em* em)
         cudaSetDevice(em->ctx->gpus[g].device);
         cudaStreamSynchronize(em->ctx->gpus[g].stream);
         EmGpu& eg = em->gpus[g];
+        eg.timer.destroy();
         for (void* ptr : {static_cast<void*>(eg.theta[0]), static_cast<void*>(eg.theta[1]), static_cast<void*>(eg.params),
                           static_cast<void*>(eg.partials), static_cast<void*>(eg.vsum), static_cast<void*>(eg.ll),
                           static_cast<void*>(eg.feat_m), static_cast<void*>(eg.feat_e), static_cast<void*>(eg.counter),
@@ -854,48 +859,78 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
     return rc;
 }
 
-int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_out)
+int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out, int64_t ld, unsigned int* labels_out)
 {
-    MLB_REQUIRE(em, "mlb_em_emit: null argument");
+    MLB_REQUIRE(em, "mlb_em_emit_range: null argument");
+    MLB_REQUIRE(begin >= 0 && count >= 0 && begin + count <= em->data->lay.n_total, "mlb_em_emit_range: range out of bounds");
     if (!em->have_step) { set_error("mlb_em_emit: no step has been run"); return MLB_ESTATE; }
-    if (!resp_out && !labels_out) return MLB_OK;
+    if ((!resp_out && !labels_out) || count == 0) return MLB_OK;
+    MLB_REQUIRE(!resp_out || ld >= count, "mlb_em_emit_range: leading dimension smaller than the row count");
     mlb_ctx* ctx = em->ctx;
-    const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
+    int64_t covered = 0;
+    for (const DataShard& sh : em->data->shards) covered += std::max<int64_t>(0, std::min(begin + count, sh.end) - std::max(begin, sh.begin));
+    MLB_REQUIRE(covered == count, "mlb_em_emit_range: range is not held by this context");
     // Stage by stage: kStagePoints points per GPU at a time through a device buffer.
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
         EmGpu& eg = em->gpus[g];
-        if (!eg.stage) MLB_CUDA(cudaMalloc(&eg.stage, sizeof(double) * kStagePoints * em->k));
-        if (!eg.stage_labels) MLB_CUDA(cudaMalloc(&eg.stage_labels, sizeof(unsigned) * kStagePoints));
+        if (resp_out && !eg.stage) MLB_CUDA(cudaMalloc(&eg.stage, sizeof(double) * kStagePoints * em->k));
+        if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMalloc(&eg.stage_labels, sizeof(unsigned) * kStagePoints));
         return MLB_OK;
     }));
-    int64_t longest = 0;
-    for (const DataShard& sh : em->data->shards) longest = std::max(longest, sh.n());
-    for (int64_t off = 0; off < longest; off += kStagePoints) {
+    for (int64_t off = 0;; off += kStagePoints) {
+        bool any = false;
         MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
             const DataShard& sh = em->data->shards[g];
-            const int64_t count = std::min<int64_t>(kStagePoints, sh.n() - off);
-            if (count <= 0) return MLB_OK;
+            const int64_t lo = std::max(begin, sh.begin) + off, hi = std::min(begin + count, sh.end);
+            const int64_t n = std::min<int64_t>(kStagePoints, hi - lo);
+            if (n <= 0) return MLB_OK;
+            any = true;
             EmGpu& eg = em->gpus[g];
             EmArgs a = base_args(em, g);
             a.theta = eg.theta[em->cur ^ 1];  // theta_t of the last step
             a.chunk = kTile;
-            a.n_chunks = static_cast<int>((count + kTile - 1) / kTile);
-            a.range_begin = off;
-            a.range_count = count;
+            a.n_chunks = static_cast<int>((n + kTile - 1) / kTile);
+            a.range_begin = lo - sh.begin;
+            a.range_count = n;
             a.r_out = resp_out ? eg.stage : nullptr;
             a.r_out_ld = kStagePoints;
             a.labels_out = labels_out ? eg.stage_labels : nullptr;
             MLB_TRY(launch_em(em, em->fn_emit, a, g, 8 * kSmCount));
-            const int64_t row = sh.begin - host_begin + off;
+            const int64_t row = lo - begin;
             if (resp_out)
-                MLB_CUDA(cudaMemcpy2DAsync(resp_out + row, sizeof(double) * ld, eg.stage, sizeof(double) * kStagePoints, sizeof(double) * count, em->k,
+                MLB_CUDA(cudaMemcpy2DAsync(resp_out + row, sizeof(double) * ld, eg.stage, sizeof(double) * kStagePoints, sizeof(double) * n, em->k,
                                            cudaMemcpyDeviceToHost, gpu.stream));
-            if (labels_out) MLB_CUDA(cudaMemcpyAsync(labels_out + row, eg.stage_labels, sizeof(unsigned) * count, cudaMemcpyDeviceToHost, gpu.stream));
+            if (labels_out) MLB_CUDA(cudaMemcpyAsync(labels_out + row, eg.stage_labels, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, gpu.stream));
             return MLB_OK;
         }));
         MLB_TRY(mlb_ctx_synchronize(ctx));
+        if (!any) break;
     }
     return MLB_OK;
+}
+
+int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_out)
+{
+    MLB_REQUIRE(em, "mlb_em_emit: null argument");
+    const std::vector<DataShard>& shards = em->data->shards;
+    return mlb_em_emit_range(em, shards.front().begin, shards.back().end - shards.front().begin, resp_out, ld, labels_out);
+}
+
+int mlb_em_set_kernel_timing(mlb_em* em, int enabled)
+{
+    MLB_REQUIRE(em, "mlb_em_set_kernel_timing: null argument");
+    for (EmGpu& eg : em->gpus) {
+        eg.timer.enabled = enabled != 0;
+        eg.timer.reset();
+    }
+    return MLB_OK;
+}
+
+int mlb_em_kernel_time_ms(mlb_em* em, double* total_ms, int64_t* launches)
+{
+    MLB_REQUIRE(em, "mlb_em_kernel_time_ms: null argument");
+    MLB_CUDA(cudaSetDevice(em->ctx->gpus[0].device));
+    return em->gpus[0].timer.total(total_ms, launches);
 }
 
 int mlb_em_last_path(const mlb_em* em, int* path)

@@ -123,6 +123,19 @@ int for_each_gpu(mlb_ctx* ctx, F&& body)
 // Fixed summation order => deterministic and independent of the GPU count.
 int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s);
 
+// Event pairs around the launches of one kernel on one stream (roofline timing for bench.py).
+struct KernelTimer {
+    bool enabled = false;
+    std::vector<cudaEvent_t> events;  // pairs
+    size_t used = 0;                  // events recorded
+    static constexpr size_t kMaxLaunches = 4096;
+    int begin(cudaStream_t stream);
+    int end(cudaStream_t stream);
+    int total(double* total_ms, int64_t* launches);
+    void reset() { used = 0; }
+    void destroy();
+};
+
 // Host-side fixed tree over the 8 virtual-shard vectors: ((0+1)+(2+3))+((4+5)+(6+7)).
 __host__ __device__ inline double tree8(const double* v, int64_t stride)
 {

@@ -344,6 +344,7 @@ struct KmGpu {
     double* out = nullptr;
     unsigned* counter = nullptr;
     int grid = 0;
+    KernelTimer timer;
 };
 
 }  // namespace mlb
@@ -436,6 +437,7 @@ int mlb_km_destroy(mlb_km* km)
         cudaSetDevice(km->ctx->gpus[g].device);
         cudaStreamSynchronize(km->ctx->gpus[g].stream);
         KmGpu& kg = km->gpus[g];
+        kg.timer.destroy();
         for (void* ptr : {static_cast<void*>(kg.craw), static_cast<void*>(kg.cold), static_cast<void*>(kg.cfrag), static_cast<void*>(kg.cnorm),
                           static_cast<void*>(kg.cmax), static_cast<void*>(kg.labels), static_cast<void*>(kg.partials), static_cast<void*>(kg.vsum),
                           static_cast<void*>(kg.out), static_cast<void*>(kg.counter)})
@@ -486,8 +488,10 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
         a.counter = kg.counter; a.accumulate = 1;
         MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
         if (a.n_chunks > 0) {
+            MLB_TRY(kg.timer.begin(gpu.stream));
             km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
             MLB_CUDA(cudaGetLastError());
+            MLB_TRY(kg.timer.end(gpu.stream));
             ++km->launches;
         }
         return MLB_OK;
@@ -546,6 +550,23 @@ int mlb_km_get_labels(mlb_km* km, unsigned int* labels)
         return MLB_OK;
     }));
     return mlb_ctx_synchronize(km->ctx);
+}
+
+int mlb_km_set_kernel_timing(mlb_km* km, int enabled)
+{
+    MLB_REQUIRE(km, "mlb_km_set_kernel_timing: null argument");
+    for (KmGpu& kg : km->gpus) {
+        kg.timer.enabled = enabled != 0;
+        kg.timer.reset();
+    }
+    return MLB_OK;
+}
+
+int mlb_km_kernel_time_ms(mlb_km* km, double* total_ms, int64_t* launches)
+{
+    MLB_REQUIRE(km, "mlb_km_kernel_time_ms: null argument");
+    MLB_CUDA(cudaSetDevice(km->ctx->gpus[0].device));
+    return km->gpus[0].timer.total(total_ms, launches);
 }
 
 int mlb_km_launch_count(const mlb_km* km, int64_t* launches)

@@ -1,0 +1,156 @@
+#pragma once
+// ml::EM: Gaussian-mixture expectation-maximisation with the reference's public surface
+// (ML/EM.hpp:18-166) on the B200 backend.  fit() copies the data to HBM (sharded over the GPUs of
+// the process-wide context), runs the fused E+M kernel once per iteration through the C-ABI of
+// include/mlb200.h, and keeps the initialisers, the pseudo-random stream and the convergence test
+// on the host exactly as the reference does (ML/EM.cpp:91-174).
+//
+// Differences from the reference header, all additive:
+//   - number_iterations(): iterations run by the last fit (requested by the north star; the
+//     reference does not store it);
+//   - responsibilities() is out of line: the N x K matrix stays on the device until first asked for
+//     (25.6 GB at N=1e8, K=32), then is materialised once; the values are the reference's.
+#include <memory>
+#include <random>
+#include <vector>
+#include <Eigen/Core>
+#include "Clustering.hpp"
+#include "dll.hpp"
+
+namespace ml
+{
+	namespace detail { class EmDevice; }
+
+	class EM: public Clustering::Model
+	{
+	public:
+		/** @throw std::invalid_argument If `number_components` is zero. */
+		DLL_DECLSPEC EM(unsigned int number_components);
+		DLL_DECLSPEC ~EM() override;
+		EM(const EM&) = delete;
+		EM& operator=(const EM&) = delete;
+
+		DLL_DECLSPEC void set_seed(unsigned int seed);
+
+		/** @throw std::domain_error If negative. */
+		DLL_DECLSPEC void set_absolute_tolerance(double absolute_tolerance);
+
+		/** @throw std::domain_error If negative. */
+		DLL_DECLSPEC void set_relative_tolerance(double relative_tolerance);
+
+		/** @throw std::invalid_argument If less than 2. */
+		DLL_DECLSPEC void set_maximum_steps(unsigned int maximum_steps);
+
+		/** @throw std::invalid_argument If null. */
+		DLL_DECLSPEC void set_means_initialiser(std::shared_ptr<const Clustering::CentroidsInitialiser> means_initialiser);
+
+		/** @throw std::invalid_argument If null. */
+		DLL_DECLSPEC void set_responsibilities_initialiser(std::shared_ptr<const Clustering::ResponsibilitiesInitialiser> responsibilities_initialiser);
+
+		void set_verbose(bool verbose)
+		{
+			verbose_ = verbose;
+		}
+
+		/** Start from an M-step on initial responsibilities instead of from initial means. */
+		void set_maximise_first(bool maximise_first)
+		{
+			maximise_first_ = maximise_first;
+		}
+
+		/** @throw std::invalid_argument If data has no rows or fewer columns than components. */
+		DLL_DECLSPEC bool fit(Eigen::Ref<const Eigen::MatrixXd> data) override;
+
+		auto number_components() const
+		{
+			return number_components_;
+		}
+
+		unsigned int number_clusters() const override
+		{
+			return number_components();
+		}
+
+		/** D x K. */
+		const auto& means() const
+		{
+			return means_;
+		}
+
+		const Eigen::MatrixXd& centroids() const override
+		{
+			return means();
+		}
+
+		const auto& covariances() const
+		{
+			return covariances_;
+		}
+
+		/** @throw std::invalid_argument If k is out of range. */
+		DLL_DECLSPEC const Eigen::MatrixXd& covariance(unsigned int k) const;
+
+		const auto& mixing_probabilities() const
+		{
+			return mixing_probabilities_;
+		}
+
+		/** N x K, from the last E-step of the fit. */
+		DLL_DECLSPEC const Eigen::MatrixXd& responsibilities() const;
+
+		double log_likelihood() const
+		{
+			return log_likelihood_;
+		}
+
+		std::shared_ptr<const Clustering::CentroidsInitialiser> means_initialiser() const
+		{
+			return means_initialiser_;
+		}
+
+		/** Responsibilities of the fitted components for a point x (u must have K entries).
+		@throw std::invalid_argument On size mismatch. */
+		DLL_DECLSPEC void assign_responsibilities(Eigen::Ref<const Eigen::VectorXd> x, Eigen::Ref<Eigen::VectorXd> u) const;
+
+		const std::vector<unsigned int>& labels() const override
+		{
+			return labels_;
+		}
+
+		bool converged() const override
+		{
+			return converged_;
+		}
+
+		/** Iterations (E-step + M-step pairs) executed by the last fit. */
+		unsigned int number_iterations() const
+		{
+			return number_iterations_;
+		}
+	private:
+		std::default_random_engine prng_;
+		std::shared_ptr<const Clustering::CentroidsInitialiser> means_initialiser_;
+		std::shared_ptr<const Clustering::ResponsibilitiesInitialiser> responsibilities_initialiser_;
+		Eigen::VectorXd mixing_probabilities_;
+		Eigen::MatrixXd means_; /**< D x K */
+		mutable Eigen::MatrixXd responsibilities_; /**< N x K, materialised on demand */
+		mutable bool responsibilities_on_host_;
+		std::vector<Eigen::MatrixXd> covariances_; /**< K matrices D x D */
+		std::vector<Eigen::MatrixXd> inverse_covariances_;
+		Eigen::VectorXd sqrt_covariance_determinants_;
+		std::vector<unsigned int> labels_;
+		double absolute_tolerance_;
+		double relative_tolerance_;
+		double log_likelihood_;
+		unsigned int number_components_;
+		unsigned int maximum_steps_;
+		unsigned int number_iterations_;
+		bool verbose_;
+		bool maximise_first_;
+		bool converged_;
+		mutable std::unique_ptr<detail::EmDevice> device_; /**< HBM-resident state of the last fit */
+
+		void process_covariances(Eigen::Index number_dimensions);
+		void fetch_parameters(Eigen::Index number_dimensions);
+	};
+}

@@ -1,0 +1,100 @@
+#pragma once
+// ml::Clustering::KMeans: Lloyd's algorithm with the reference's public surface
+// (ML/KMeans.hpp:19-101) on the B200 backend; number_iterations() is the one addition.
+#include "Clustering.hpp"
+#include <memory>
+#include <vector>
+#include <utility>
+#include <Eigen/Core>
+#include "dll.hpp"
+
+namespace ml
+{
+    namespace detail { class KmDevice; }
+
+    namespace Clustering
+    {
+        class KMeans : public Model
+        {
+        public:
+            /** @throw std::invalid_argument If `number_clusters` is zero. */
+            DLL_DECLSPEC KMeans(unsigned int number_clusters);
+            DLL_DECLSPEC ~KMeans() override;
+            KMeans(const KMeans&) = delete;
+            KMeans& operator=(const KMeans&) = delete;
+
+            DLL_DECLSPEC bool fit(Eigen::Ref<const Eigen::MatrixXd> data) override;
+
+            unsigned int number_clusters() const override
+            {
+                return num_clusters_;
+            }
+
+            const std::vector<unsigned int>& labels() const override
+            {
+                return labels_;
+            }
+
+            const Eigen::MatrixXd& centroids() const override
+            {
+                return centroids_;
+            }
+
+            DLL_DECLSPEC void set_seed(unsigned int seed);
+
+            /** Tolerance on the squared Frobenius norm of the centroid shift.
+            @throw std::domain_error If negative. */
+            DLL_DECLSPEC void set_absolute_tolerance(double absolute_tolerance);
+
+            /** @throw std::invalid_argument If less than 2. */
+            DLL_DECLSPEC void set_maximum_steps(unsigned int maximum_steps);
+
+            /** @throw std::invalid_argument If zero. */
+            DLL_DECLSPEC void set_number_initialisations(unsigned int number_initialisations);
+
+            /** @throw std::invalid_argument If null. */
+            DLL_DECLSPEC void set_centroids_initialiser(std::shared_ptr<const CentroidsInitialiser> centroids_initialiser);
+
+            void set_verbose(bool verbose)
+            {
+                verbose_ = verbose;
+            }
+
+            /** Nearest centroid of x and the squared distance to it.
+            @throw std::invalid_argument If x has the wrong size. */
+            DLL_DECLSPEC std::pair<unsigned int, double> assign_label(Eigen::Ref<const Eigen::VectorXd> x) const;
+
+            /** Sum of squared distances of the points to their centroids. */
+            double inertia() const
+            {
+                return inertia_;
+            }
+
+            bool converged() const override
+            {
+                return converged_;
+            }
+
+            /** Assignment steps executed by the last (single-initialisation) fit. */
+            unsigned int number_iterations() const
+            {
+                return number_iterations_;
+            }
+        private:
+            std::vector<unsigned int> labels_;
+            Eigen::MatrixXd centroids_;
+            std::default_random_engine prng_;
+            std::shared_ptr<const CentroidsInitialiser> centroids_initialiser_;
+            double absolute_tolerance_;
+            double inertia_;
+            unsigned int maximum_steps_;
+            unsigned int num_inits_;
+            unsigned int num_clusters_;
+            unsigned int number_iterations_;
+            bool verbose_;
+            bool converged_;
+
+            bool fit_once(Eigen::Ref<const Eigen::MatrixXd> data, detail::KmDevice& device);
+        };
+    }
+}

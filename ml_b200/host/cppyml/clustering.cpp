@@ -1,0 +1,190 @@
+// cppyml.clustering: the Python surface of the reference's cppyml/clustering.cpp:75-184 over the
+// B200 host classes.  Same class names, methods, properties, argument names and array conventions:
+// fit() takes a float64 C-contiguous (N, D) array without conversion (a point per row) and views it
+// as the column-major D x N matrix the C++ API wants; `means` is (D, K); `responsibilities` is
+// (N, K); KMeans.centroids is (K, D); KMeans.labels is a list.
+//
+// pybind11/eigen.h needs the real Eigen headers; so that the module also builds where Eigen is not
+// installed, arrays are converted by hand through pybind11/numpy.h (same shapes, same dtypes).
+#include <pybind11/pybind11.h>
+#include <pybind11/numpy.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <stdexcept>
+
+#include "ML/Clustering.hpp"
+#include "ML/EM.hpp"
+#include "ML/KMeans.hpp"
+
+namespace py = pybind11;
+
+namespace
+{
+	using MatrixXdR = Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>;
+
+	/** The (N, D) row-major array as a D x N column-major matrix, without copying. */
+	Eigen::Map<const Eigen::MatrixXd> as_columns(const py::array& data)
+	{
+		if (!py::isinstance<py::array_t<double>>(data) || data.ndim() != 2 || !(data.flags() & py::array::c_style)) {
+			throw py::type_error("fit(): incompatible function arguments. data must be a C-contiguous float64 numpy array of shape (N, D); no conversion is performed");
+		}
+		return Eigen::Map<const Eigen::MatrixXd>(static_cast<const double*>(data.data()), data.shape(1), data.shape(0));
+	}
+
+	Eigen::VectorXd as_vector(const py::array_t<double, py::array::c_style | py::array::forcecast>& x)
+	{
+		if (x.ndim() != 1) {
+			throw py::type_error("x must be a 1-D array");
+		}
+		Eigen::VectorXd v(x.shape(0));
+		std::memcpy(v.data(), x.data(), sizeof(double) * static_cast<size_t>(x.shape(0)));
+		return v;
+	}
+
+	/** Column-major matrix -> numpy array of the same shape (Fortran order, like pybind11/eigen.h produces). */
+	py::array_t<double> to_numpy(const Eigen::MatrixXd& m)
+	{
+		py::array_t<double, py::array::f_style> out({m.rows(), m.cols()});
+		std::memcpy(out.mutable_data(), m.data(), sizeof(double) * static_cast<size_t>(m.size()));
+		return out;
+	}
+
+	py::array_t<double> to_numpy(const Eigen::VectorXd& v)
+	{
+		py::array_t<double> out(v.size());
+		std::memcpy(out.mutable_data(), v.data(), sizeof(double) * static_cast<size_t>(v.size()));
+		return out;
+	}
+}
+
+namespace ml
+{
+	/** ml::EM with row-major entry points for Python. */
+	class EMPy : public EM
+	{
+	public:
+		explicit EMPy(unsigned int number_components)
+			: EM(number_components)
+		{}
+
+		bool fit_row_major(const py::array& data)
+		{
+			const auto columns = as_columns(data);
+			py::gil_scoped_release release;   // no Python callbacks happen inside fit
+			return fit(columns);
+		}
+
+		py::array_t<double> calculate_responsibilities(const py::array_t<double, py::array::c_style | py::array::forcecast>& x) const
+		{
+			const Eigen::VectorXd point = as_vector(x);
+			Eigen::VectorXd u(number_components());
+			EM::assign_responsibilities(point, u);
+			return to_numpy(u);
+		}
+	};
+
+	namespace Clustering
+	{
+		/** ml::Clustering::KMeans with row-major entry points for Python. */
+		class KMeansPy : public KMeans
+		{
+		public:
+			explicit KMeansPy(unsigned int number_clusters)
+				: KMeans(number_clusters)
+			{}
+
+			bool fit_row_major(const py::array& data)
+			{
+				const auto columns = as_columns(data);
+				py::gil_scoped_release release;
+				return fit(columns);
+			}
+
+			/** (K, D), C order: the memory of the D x K column-major centroid matrix. */
+			py::array_t<double> centroids_row_major() const
+			{
+				const Eigen::MatrixXd& c = centroids();
+				py::array_t<double> out({c.cols(), c.rows()});
+				std::memcpy(out.mutable_data(), c.data(), sizeof(double) * static_cast<size_t>(c.size()));
+				return out;
+			}
+
+			std::pair<unsigned int, double> assign_label_py(const py::array_t<double, py::array::c_style | py::array::forcecast>& x) const
+			{
+				return assign_label(as_vector(x));
+			}
+		};
+	}
+}
+
+void init_clustering(py::module_& m)
+{
+	auto m_clustering = m.def_submodule("clustering", "Clustering algorithms.");
+
+	py::class_<ml::Clustering::CentroidsInitialiser, std::shared_ptr<ml::Clustering::CentroidsInitialiser>>(m_clustering, "CentroidsInitialiser")
+		.doc() = "Abstract centroids initialiser.";
+
+	py::class_<ml::Clustering::ResponsibilitiesInitialiser, std::shared_ptr<ml::Clustering::ResponsibilitiesInitialiser>>(m_clustering, "ResponsibilitiesInitialiser")
+		.doc() = "Abstract responsibilities initialiser.";
+
+	py::class_<ml::Clustering::Forgy, std::shared_ptr<ml::Clustering::Forgy>, ml::Clustering::CentroidsInitialiser>(m_clustering, "Forgy")
+		.def(py::init<>())
+		.doc() = "Forgy initialisation algorithm.";
+
+	py::class_<ml::Clustering::RandomPartition, std::shared_ptr<ml::Clustering::RandomPartition>, ml::Clustering::CentroidsInitialiser>(m_clustering, "RandomPartition")
+		.def(py::init<>())
+		.doc() = "Random Partition initialisation algorithm.";
+
+	py::class_<ml::Clustering::KPP, std::shared_ptr<ml::Clustering::KPP>, ml::Clustering::CentroidsInitialiser>(m_clustering, "KPP")
+		.def(py::init<>())
+		.doc() = "KMeans++ initialisation algorithm.";
+
+	py::class_<ml::Clustering::ClosestCentroid, std::shared_ptr<ml::Clustering::ClosestCentroid>, ml::Clustering::ResponsibilitiesInitialiser>(m_clustering, "ClosestCentroid")
+		.def(py::init<std::shared_ptr<ml::Clustering::CentroidsInitialiser>>(), py::arg("centroids_initialiser"))
+		.doc() = "Initialises responsibilities by assigning every point to its closest initial centroid.";
+
+	py::class_<ml::EMPy, std::shared_ptr<ml::EMPy>>(m_clustering, "EM")
+		.def(py::init<unsigned int>(), py::arg("number_components"), "Constructor.\n\nArgs:\n    number_components: Number of Gaussian components, > 0.")
+		.def("set_seed", &ml::EMPy::set_seed, py::arg("seed"), "Sets PRNG seed.")
+		.def("set_absolute_tolerance", &ml::EMPy::set_absolute_tolerance, py::arg("absolute_tolerance"), "Sets absolute tolerance.")
+		.def("set_relative_tolerance", &ml::EMPy::set_relative_tolerance, py::arg("relative_tolerance"), "Sets relative tolerance.")
+		.def("set_maximum_steps", &ml::EMPy::set_maximum_steps, py::arg("maximum_steps"), "Sets maximum number of iterations.")
+		.def("set_means_initialiser", &ml::EMPy::set_means_initialiser, py::arg("means_initialiser"), "Sets the algorithm to initialise component means.")
+		.def("set_responsibilities_initialiser", &ml::EMPy::set_responsibilities_initialiser, py::arg("responsibilities_initialiser"), "Sets the algorithm to initialise responsibilities.")
+		.def("set_verbose", &ml::EMPy::set_verbose, py::arg("verbose"), "Turns on/off the verbose mode.")
+		.def("set_maximise_first", &ml::EMPy::set_maximise_first, py::arg("maximise_first"), "Turns on/off doing an initial maximisation step before the E-M iterations.")
+		.def("fit", &ml::EMPy::fit_row_major, py::arg("data").noconvert(),
+			"Fits the components to the data.\n\nArgs:\n    data: A 2D array with data points in rows.\n\nReturns:\n    True if EM algorithm converged.")
+		.def_property_readonly("number_components", &ml::EMPy::number_components, "Number of Gaussian components.")
+		.def_property_readonly("means", [](const ml::EMPy& em) { return to_numpy(em.means()); }, "Fitted means.")
+		.def_property_readonly("responsibilities", [](const ml::EMPy& em) { return to_numpy(em.responsibilities()); }, "Fitted responsibilities.")
+		.def_property_readonly("log_likelihood", &ml::EMPy::log_likelihood, "Maximised log-likelihood.")
+		.def_property_readonly("mixing_probabilities", [](const ml::EMPy& em) { return to_numpy(em.mixing_probabilities()); }, "Mixing probabilities of components.")
+		.def_property_readonly("number_iterations", &ml::EMPy::number_iterations, "Iterations run by the last fit.")
+		.def("covariance", [](const ml::EMPy& em, unsigned int k) { return to_numpy(em.covariance(k)); }, py::arg("k"),
+			"Returns k-th covariance matrix.\n\nArgs:\n    k: Component index.\n\nReturns:\n    2D square matrix.")
+		.def("assign_responsibilities", &ml::EMPy::calculate_responsibilities, py::arg("x"),
+			"Given a data point x, calculate each component's responsibilities for x and return them.\n\nArgs:\n    x: Data point with correct number of dimensions.\n\nReturns:\n    1D array of responsibilities.")
+		.doc() = "Gaussian Expectation-Maximisation algorithm.";
+
+	py::class_<ml::Clustering::KMeansPy, std::shared_ptr<ml::Clustering::KMeansPy>>(m_clustering, "KMeans")
+		.def(py::init<unsigned int>(), py::arg("number_clusters"), "Constructor.\n\nArgs:\n    number_clusters: Number of clusters, > 0.")
+		.def("set_seed", &ml::Clustering::KMeansPy::set_seed, py::arg("seed"), "Sets the PRNG seed.")
+		.def("set_absolute_tolerance", &ml::Clustering::KMeansPy::set_absolute_tolerance, py::arg("absolute_tolerance"), "Sets absolute tolerance.")
+		.def("set_maximum_steps", &ml::Clustering::KMeansPy::set_maximum_steps, py::arg("maximum_steps"), "Sets maximum number of iterations.")
+		.def("set_centroids_initialiser", &ml::Clustering::KMeansPy::set_centroids_initialiser, py::arg("centroids_initialiser"), "Sets the algorithm to initialise centroids.")
+		.def("set_number_initialisations", &ml::Clustering::KMeansPy::set_number_initialisations, py::arg("centroids_initialiser"), "Sets number of initialisations.")
+		.def("set_verbose", &ml::Clustering::KMeansPy::set_verbose, py::arg("verbose"), "Turns on/off the verbose mode.")
+		.def("fit", &ml::Clustering::KMeansPy::fit_row_major, py::arg("data").noconvert(),
+			"Fits the components to the data.\n\nArgs:\n    data: A 2D array with data points in rows.\n\nReturns:\n    True if K-means algorithm converged.")
+		.def_property_readonly("number_clusters", &ml::Clustering::KMeansPy::number_clusters, "Number of clusters.")
+		.def_property_readonly("centroids", &ml::Clustering::KMeansPy::centroids_row_major, "Fitted centroids.")
+		.def_property_readonly("labels", &ml::Clustering::KMeansPy::labels, "Fitted labels.")
+		.def_property_readonly("inertia", &ml::Clustering::KMeansPy::inertia, "Minimised inertia.")
+		.def_property_readonly("converged", &ml::Clustering::KMeansPy::converged, "Whether the last fit converged.")
+		.def_property_readonly("number_iterations", &ml::Clustering::KMeansPy::number_iterations, "Assignment steps run by the last fit.")
+		.def("assign_label", &ml::Clustering::KMeansPy::assign_label_py, py::arg("x"),
+			"Given a data point x, assigns it to the closest cluster.\n\nArgs:\n    x: Data point with correct number of dimensions.\n\nReturns:\n    Tuple of cluster label and squared Euclidean distance to cluster centroid.")
+		.doc() = "K-means clustering algorithm.";
+}

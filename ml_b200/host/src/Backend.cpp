@@ -1,0 +1,179 @@
+#include "Backend.hpp"
+
+#include <cstdlib>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+namespace ml
+{
+	namespace detail
+	{
+		void check(int status, const char* where)
+		{
+			if (status == MLB_OK) {
+				return;
+			}
+			const std::string message = std::string(where) + ": " + mlb_last_error();
+			if (status == MLB_EINVAL) {
+				throw std::invalid_argument(message);
+			}
+			throw std::runtime_error(message);
+		}
+
+		namespace
+		{
+			struct ContextHolder
+			{
+				mlb_ctx* ctx = nullptr;
+				~ContextHolder()
+				{
+					if (ctx) {
+						mlb_ctx_destroy(ctx);
+					}
+				}
+			};
+		}
+
+		mlb_ctx* shared_context()
+		{
+			static ContextHolder holder;
+			static std::mutex mutex;
+			std::lock_guard<std::mutex> lock(mutex);
+			if (!holder.ctx) {
+				int number_devices = 1;
+				if (const char* env = std::getenv("MLPP_CUDA_DEVICES")) {
+					number_devices = std::atoi(env);
+				}
+				check(mlb_ctx_create(nullptr, number_devices, &holder.ctx), "ML++ B200 backend");
+			}
+			return holder.ctx;
+		}
+
+		DeviceData::DeviceData(Eigen::Ref<const Eigen::MatrixXd> data)
+			: rows_(data.rows()), cols_(data.cols())
+		{
+			check(mlb_data_upload(shared_context(), data.data(), data.cols(), data.cols(), static_cast<int>(data.rows()), data.outerStride(), &handle_), "upload");
+		}
+
+		DeviceData::~DeviceData()
+		{
+			mlb_data_free(handle_);
+		}
+
+		EmDevice::EmDevice(Eigen::Ref<const Eigen::MatrixXd> data, unsigned int number_components)
+			: data_(data), number_components_(number_components)
+		{
+			check(mlb_em_create(shared_context(), data_.handle(), static_cast<int>(number_components), &em_), "EM");
+		}
+
+		EmDevice::~EmDevice()
+		{
+			mlb_em_destroy(em_);
+		}
+
+		Eigen::MatrixXd EmDevice::sample_covariance()
+		{
+			Eigen::MatrixXd covariance(data_.rows(), data_.rows());
+			check(mlb_em_sample_covariance(em_, covariance.data()), "EM sample covariance");
+			return covariance;
+		}
+
+		void EmDevice::set_parameters(const Eigen::MatrixXd& means, const std::vector<Eigen::MatrixXd>& covariances, const Eigen::VectorXd& mixing_probabilities)
+		{
+			const auto dd = static_cast<size_t>(data_.rows() * data_.rows());
+			std::vector<double> packed(dd * covariances.size());
+			for (size_t k = 0; k < covariances.size(); ++k) {
+				std::copy(covariances[k].data(), covariances[k].data() + dd, packed.begin() + static_cast<std::ptrdiff_t>(k * dd));
+			}
+			check(mlb_em_set_params(em_, means.data(), packed.data(), mixing_probabilities.data()), "EM parameters");
+		}
+
+		void EmDevice::maximise_from(const Eigen::MatrixXd& responsibilities)
+		{
+			check(mlb_em_mstep_from_responsibilities(em_, responsibilities.data(), responsibilities.rows()), "EM maximisation step");
+		}
+
+		double EmDevice::step()
+		{
+			double log_likelihood = 0;
+			check(mlb_em_step(em_, &log_likelihood), "EM step");
+			return log_likelihood;
+		}
+
+		void EmDevice::get_parameters(Eigen::MatrixXd& means, std::vector<Eigen::MatrixXd>& covariances, Eigen::VectorXd& mixing_probabilities)
+		{
+			const Eigen::Index d = data_.rows();
+			const auto dd = static_cast<size_t>(d * d);
+			std::vector<double> packed(dd * number_components_);
+			means.resize(d, number_components_);
+			mixing_probabilities.resize(number_components_);
+			check(mlb_em_get_params(em_, means.data(), packed.data(), mixing_probabilities.data()), "EM parameters");
+			covariances.resize(number_components_);
+			for (size_t k = 0; k < covariances.size(); ++k) {
+				covariances[k].resize(d, d);
+				std::copy(packed.begin() + static_cast<std::ptrdiff_t>(k * dd), packed.begin() + static_cast<std::ptrdiff_t>((k + 1) * dd), covariances[k].data());
+			}
+		}
+
+		void EmDevice::emit(Eigen::MatrixXd* responsibilities, std::vector<unsigned int>* labels)
+		{
+			if (responsibilities) {
+				responsibilities->resize(data_.cols(), number_components_);
+			}
+			if (labels) {
+				labels->resize(static_cast<size_t>(data_.cols()));
+			}
+			check(mlb_em_emit(em_, responsibilities ? responsibilities->data() : nullptr, data_.cols(), labels ? labels->data() : nullptr), "EM responsibilities");
+		}
+
+		void EmDevice::emit_rows(Eigen::Index begin, Eigen::Index count, Eigen::MatrixXd& responsibilities)
+		{
+			responsibilities.resize(count, number_components_);
+			check(mlb_em_emit_range(em_, begin, count, responsibilities.data(), count, nullptr), "EM responsibilities");
+		}
+
+		KmDevice::KmDevice(Eigen::Ref<const Eigen::MatrixXd> data, unsigned int number_clusters)
+			: data_(data)
+		{
+			check(mlb_km_create(shared_context(), data_.handle(), static_cast<int>(number_clusters), &km_), "KMeans");
+		}
+
+		KmDevice::~KmDevice()
+		{
+			mlb_km_destroy(km_);
+		}
+
+		void KmDevice::set_centroids(const Eigen::MatrixXd& centroids)
+		{
+			check(mlb_km_set_centroids(km_, centroids.data()), "KMeans centroids");
+		}
+
+		void KmDevice::get_centroids(Eigen::MatrixXd& centroids)
+		{
+			check(mlb_km_get_centroids(km_, centroids.data()), "KMeans centroids");
+		}
+
+		double KmDevice::assign(std::int64_t& changed)
+		{
+			double inertia = 0;
+			int64_t n_changed = 0;
+			check(mlb_km_assign(km_, &inertia, &n_changed), "KMeans assignment step");
+			changed = n_changed;
+			return inertia;
+		}
+
+		double KmDevice::update()
+		{
+			double shift = 0;
+			check(mlb_km_update(km_, &shift), "KMeans update step");
+			return shift;
+		}
+
+		void KmDevice::get_labels(std::vector<unsigned int>& labels)
+		{
+			labels.resize(static_cast<size_t>(data_.cols()));
+			check(mlb_km_get_labels(km_, labels.data()), "KMeans labels");
+		}
+	}
+}

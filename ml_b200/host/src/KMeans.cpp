@@ -1,0 +1,187 @@
+// ml::Clustering::KMeans on the B200 backend.  Control flow, defaults and error behaviour follow
+// ML/KMeans.cpp:11-151; assignment_step and update_step (KMeans.cpp:153-192) run on the device.
+// The data is uploaded once per fit() and shared by all initialisations of a multi-start fit.
+#include "ML/KMeans.hpp"
+
+#include <algorithm>
+#include <iostream>
+#include <limits>
+#include <stdexcept>
+
+#include "Backend.hpp"
+
+namespace ml
+{
+	namespace Clustering
+	{
+		KMeans::KMeans(unsigned int number_clusters)
+			: centroids_initialiser_(std::make_shared<Forgy>())
+			, absolute_tolerance_(1e-8)
+			, inertia_(0)
+			, maximum_steps_(1000)
+			, num_inits_(1)
+			, num_clusters_(number_clusters)
+			, number_iterations_(0)
+			, verbose_(false)
+			, converged_(false)
+		{
+			if (!number_clusters) {
+				throw std::invalid_argument("KMeans: number of clusters must be positive");
+			}
+		}
+
+		KMeans::~KMeans() = default;
+
+		bool KMeans::fit(Eigen::Ref<const Eigen::MatrixXd> data)
+		{
+			const auto number_dimensions = static_cast<unsigned int>(data.rows());
+			const auto sample_size = static_cast<unsigned int>(data.cols());
+			if (!number_dimensions) {
+				throw std::invalid_argument("KMeans: At least one dimension required");
+			}
+			if (sample_size < num_clusters_) {
+				throw std::invalid_argument("KMeans: Not enough data ");
+			}
+			converged_ = false;
+			number_iterations_ = 0;
+			centroids_.resize(number_dimensions, num_clusters_);
+			labels_.resize(sample_size);
+
+			if (sample_size == num_clusters_) {
+				// Every point is its own cluster (KMeans.cpp:67-75); identical for every initialisation.
+				for (unsigned int i = 0; i < sample_size; ++i) {
+					std::copy_n(data.data() + static_cast<Eigen::Index>(i) * data.outerStride(), number_dimensions, centroids_.data() + static_cast<Eigen::Index>(i) * number_dimensions);
+					labels_[i] = i;
+				}
+				inertia_ = 0;
+				converged_ = true;
+				return converged_;
+			}
+
+			detail::KmDevice device(data, num_clusters_);
+			if (num_inits_ == 1) {
+				fit_once(data, device);
+			} else {
+				// Best of num_inits_ runs by inertia (KMeans.cpp:29-47).
+				double min_inertia = std::numeric_limits<double>::infinity();
+				Eigen::MatrixXd best_centroids;
+				bool any_converged = false;
+				for (unsigned int i = 0; i < num_inits_; ++i) {
+					if (fit_once(data, device)) {
+						if (inertia_ < min_inertia) {
+							min_inertia = inertia_;
+							best_centroids = centroids_;
+						}
+						any_converged = true;
+					}
+				}
+				converged_ = any_converged;
+				if (converged_) {
+					centroids_ = best_centroids;
+					device.set_centroids(centroids_);
+					std::int64_t changed = 0;
+					inertia_ = device.assign(changed);
+				}
+			}
+			device.get_labels(labels_);
+			return converged_;
+		}
+
+		bool KMeans::fit_once(Eigen::Ref<const Eigen::MatrixXd> data, detail::KmDevice& device)
+		{
+			converged_ = false;
+			centroids_initialiser_->init(data, prng_, num_clusters_, centroids_);
+			device.set_centroids(centroids_);
+			for (unsigned int step = 0; step < maximum_steps_; ++step) {
+				std::int64_t changed = 0;
+				inertia_ = device.assign(changed);
+				number_iterations_ = step + 1;
+				if (step > 0 && changed == 0) {
+					// old_labels_ == labels_ (KMeans.cpp:84-89): the centroids are not updated again
+					converged_ = true;
+					break;
+				}
+				const double centroid_shift = device.update();
+				if (verbose_) {
+					device.get_centroids(centroids_);
+					std::cout << "Step " << step << "\n";
+					for (unsigned int k = 0; k < num_clusters_; ++k) {
+						std::cout << "Centroid[" << k << "] ==";
+						for (Eigen::Index l = 0; l < centroids_.rows(); ++l) {
+							std::cout << " " << centroids_(l, k);
+						}
+						std::cout << "\n";
+					}
+					std::cout << std::endl;
+				}
+				if (step > 0 && centroid_shift < absolute_tolerance_) {
+					inertia_ = device.assign(changed);
+					converged_ = true;
+					break;
+				}
+			}
+			device.get_centroids(centroids_);
+			return converged_;
+		}
+
+		void KMeans::set_seed(unsigned int seed)
+		{
+			prng_.seed(seed);
+		}
+
+		void KMeans::set_absolute_tolerance(double absolute_tolerance)
+		{
+			if (absolute_tolerance < 0) {
+				throw std::domain_error("KMeans: Negative absolute tolerance");
+			}
+			absolute_tolerance_ = absolute_tolerance;
+		}
+
+		void KMeans::set_maximum_steps(unsigned int maximum_steps)
+		{
+			if (maximum_steps < 2) {
+				throw std::invalid_argument("KMeans: At least two steps required for convergence test");
+			}
+			maximum_steps_ = maximum_steps;
+		}
+
+		void KMeans::set_number_initialisations(unsigned int number_initialisations)
+		{
+			if (number_initialisations < 1) {
+				throw std::invalid_argument("KMeans: At least 1 initialisation required");
+			}
+			num_inits_ = number_initialisations;
+		}
+
+		void KMeans::set_centroids_initialiser(std::shared_ptr<const CentroidsInitialiser> centroids_initialiser)
+		{
+			if (!centroids_initialiser) {
+				throw std::invalid_argument("KMeans: Null centroids initialiser");
+			}
+			centroids_initialiser_ = centroids_initialiser;
+		}
+
+		std::pair<unsigned int, double> KMeans::assign_label(Eigen::Ref<const Eigen::VectorXd> x) const
+		{
+			if (x.size() != centroids_.rows()) {
+				throw std::invalid_argument("KMeans: wrong size of x");
+			}
+			const Eigen::Index dim = centroids_.rows();
+			unsigned int label = 0;
+			double smallest = std::numeric_limits<double>::infinity();
+			for (unsigned int k = 0; k < num_clusters_; ++k) {
+				const double* c = centroids_.data() + static_cast<Eigen::Index>(k) * dim;
+				double distance = 0;
+				for (Eigen::Index l = 0; l < dim; ++l) {
+					const double diff = x[l] - c[l];
+					distance += diff * diff;
+				}
+				if (distance < smallest) {
+					smallest = distance;
+					label = k;
+				}
+			}
+			return std::make_pair(label, smallest);
+		}
+	}
+}
