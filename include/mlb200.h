@@ -54,6 +54,10 @@ int mlb_version(void);                 /* 10000*major + 100*minor + patch */
 const char* mlb_last_error(void);      /* thread-local, never NULL */
 int mlb_device_count(int* count);      /* cudaGetDeviceCount */
 
+/* Diagnostic: evaluates the kernels' own FP64 exp (arguments <= 0, ml_b200/csrc/fastmath.cuh) for n host
+ * values on device 0, so that tests can bound its error against libm.  Replaces std::exp of EM.cpp:206. */
+int mlb_selftest_exp(const double* x, int64_t n, double* out);
+
 /* ---------------------------------------------------------------- context */
 
 /* One process driving n_devices local GPUs (n_devices in {1,2,4,8}); devices == NULL means

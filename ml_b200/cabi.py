@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmlb200.so")
+# MLB200_LIB: developer override used to time experimental builds of the same library (never a fallback).
+LIB_PATH = os.environ.get("MLB200_LIB") or os.path.join(_HERE, "lib", "libmlb200.so")
 
 MLB_OK, MLB_EINVAL, MLB_ECUDA, MLB_ENCCL, MLB_ENOMEM, MLB_ESTATE = range(6)
 
@@ -29,6 +30,7 @@ SIGNATURES = {
     "mlb_version": (ctypes.c_int, []),
     "mlb_last_error": (ctypes.c_char_p, []),
     "mlb_device_count": (ctypes.c_int, [_c_ip]),
+    "mlb_selftest_exp": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
     "mlb_ctx_create": (ctypes.c_int, [_c_ip, ctypes.c_int, ctypes.POINTER(_vp)]),
     "mlb_nccl_unique_id": (ctypes.c_int, [_vp]),
     "mlb_ctx_create_rank": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(_vp)]),
@@ -109,6 +111,14 @@ def device_count():
     n = ctypes.c_int()
     check(lib().mlb_device_count(ctypes.byref(n)))
     return n.value
+
+
+def selftest_exp(x):
+    """The kernels' FP64 exp for arguments <= 0, evaluated on device 0 (diagnostic)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    check(lib().mlb_selftest_exp(x.ctypes.data, x.size, out.ctypes.data))
+    return out
 
 
 def shard_range(n_total, world, rank):

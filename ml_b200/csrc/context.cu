@@ -1,9 +1,14 @@
 // Contexts (GPU sets), the resident point matrix, the synthetic generator and the deterministic
 // partial-statistics reduction + exchange shared by the EM and K-means paths.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <random>
+#include <type_traits>
 
 #include "internal.h"
 
@@ -19,6 +24,40 @@ void set_error(const char* fmt, ...)
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
     g_last_error = buf;
+}
+
+const NcclApi* nccl()
+{
+    static NcclApi api{};
+    static bool ok = false;
+    static std::string why;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the process already has (PyTorch's)
+        if (!h) {
+            const char* env = std::getenv("MLB200_NCCL_LIB");
+            if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+        }
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { why = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        bool all = true;
+        auto bind = [&](auto& fn, const char* name) {
+            fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(h, name));
+            if (!fn) { all = false; why = std::string("libnccl.so.2 lacks ") + name; }
+        };
+        bind(api.GetUniqueId, "ncclGetUniqueId");
+        bind(api.CommInitAll, "ncclCommInitAll");
+        bind(api.CommInitRank, "ncclCommInitRank");
+        bind(api.CommDestroy, "ncclCommDestroy");
+        bind(api.AllGather, "ncclAllGather");
+        bind(api.GroupStart, "ncclGroupStart");
+        bind(api.GroupEnd, "ncclGroupEnd");
+        bind(api.GetErrorString, "ncclGetErrorString");
+        bind(api.GetVersion, "ncclGetVersion");
+        ok = all;
+    });
+    if (!ok) { set_error("NCCL unavailable: %s", why.c_str()); return nullptr; }
+    return &api;
 }
 
 int KernelTimer::begin(cudaStream_t stream)
@@ -132,13 +171,14 @@ int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, co
     }));
     if (ctx->world > 1) {
         // ONE collective per iteration: every GPU contributes its 8/G shard vectors, in place.
-        MLB_NCCL(ncclGroupStart());
+        MLB_NCCL_API(api);
+        MLB_NCCL(api, api->GroupStart());
         for (size_t g = 0; g < ctx->gpus.size(); ++g) {
             Gpu& gpu = ctx->gpus[g];
             const size_t count = static_cast<size_t>(vpg) * s;
-            MLB_NCCL(ncclAllGather(vsum[g] + static_cast<int64_t>(gpu.rank) * count, vsum[g], count, ncclDouble, gpu.comm, gpu.stream));
+            MLB_NCCL(api, api->AllGather(vsum[g] + static_cast<int64_t>(gpu.rank) * count, vsum[g], count, ncclDouble, gpu.comm, gpu.stream));
         }
-        MLB_NCCL(ncclGroupEnd());
+        MLB_NCCL(api, api->GroupEnd());
     }
     return MLB_OK;
 }
@@ -331,10 +371,12 @@ int mlb_ctx_create(const int* devices, int n_devices, mlb_ctx** out)
         if (rc != MLB_OK) { delete ctx; return rc; }
     }
     if (n_devices > 1) {
+        const NcclApi* api = nccl();
+        if (!api) { delete ctx; return MLB_ENCCL; }
         std::vector<ncclComm_t> comms(n_devices);
-        ncclResult_t r = ncclCommInitAll(comms.data(), n_devices, devs.data());
+        ncclResult_t r = api->CommInitAll(comms.data(), n_devices, devs.data());
         if (r != ncclSuccess) {
-            set_error("ncclCommInitAll failed: %s", ncclGetErrorString(r));
+            set_error("ncclCommInitAll failed: %s", api->GetErrorString(r));
             delete ctx;
             return MLB_ENCCL;
         }
@@ -349,7 +391,8 @@ int mlb_nccl_unique_id(void* out128)
     MLB_REQUIRE(out128, "mlb_nccl_unique_id: null output");
     static_assert(sizeof(ncclUniqueId) == MLB_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId size");
     ncclUniqueId id;
-    MLB_NCCL(ncclGetUniqueId(&id));
+    MLB_NCCL_API(api);
+    MLB_NCCL(api, api->GetUniqueId(&id));
     std::memcpy(out128, &id, sizeof(id));
     return MLB_OK;
 }
@@ -374,9 +417,11 @@ int mlb_ctx_create_rank(int device, int rank, int world, const void* nccl_unique
     if (world > 1) {
         ncclUniqueId id;
         std::memcpy(&id, nccl_unique_id128, sizeof(id));
-        ncclResult_t r = ncclCommInitRank(&ctx->gpus[0].comm, world, id, rank);
+        const NcclApi* api = nccl();
+        if (!api) { delete ctx; return MLB_ENCCL; }
+        ncclResult_t r = api->CommInitRank(&ctx->gpus[0].comm, world, id, rank);
         if (r != ncclSuccess) {
-            set_error("ncclCommInitRank failed: %s", ncclGetErrorString(r));
+            set_error("ncclCommInitRank failed: %s", api->GetErrorString(r));
             delete ctx;
             return MLB_ENCCL;
         }
@@ -391,7 +436,7 @@ int mlb_ctx_destroy(mlb_ctx* ctx)
     for (Gpu& gpu : ctx->gpus) {
         cudaSetDevice(gpu.device);
         if (gpu.stream) cudaStreamSynchronize(gpu.stream);
-        if (gpu.comm) ncclCommDestroy(gpu.comm);
+        if (gpu.comm && nccl()) nccl()->CommDestroy(gpu.comm);
         if (gpu.ev0) cudaEventDestroy(gpu.ev0);
         if (gpu.ev1) cudaEventDestroy(gpu.ev1);
         if (gpu.stream) cudaStreamDestroy(gpu.stream);

@@ -20,23 +20,45 @@
 #include <cstring>
 #include <limits>
 
+#include "fastmath.cuh"
 #include "internal.h"
 
 namespace mlb {
 
 constexpr int kTile = 64;        // points per CTA tile
 constexpr int kEmThreads = 128;  // 4 warps
+constexpr int kLogBatch = 16;    // tiles between two log() calls of the log-likelihood partial
+
+#ifdef MLB_EM_LIBM_EXP
+#define MLB_EM_EXP(x) exp(x)
+#else
+#define MLB_EM_EXP(x) exp_nonpositive((x), etab)
+#endif
+#ifndef MLB_EM_MINB_SMALL
+#define MLB_EM_MINB_SMALL 4
+#endif
 
 // ---- compile-time shape helpers -------------------------------------------------------------
-// E-step contraction steps (4 features each): for a in [0,DP), for m in [a/4, DP/4): lane c holds
-// z_a * z_{4m+c}; then DP/4 linear steps: lane c holds z_{4m+c}.
-__host__ __device__ constexpr int em_estep_index(int DP, int a, int m)
+// E-step contraction steps.  One step feeds 4 features (one per lane c = lane & 3 of a quad) of 8 points to a
+// DMMA.8x8x4.  With the D coordinates cut into DQ = DP/4 blocks of 4, the D(D+1)/2 + D features are packed as
+//   off-diagonal block pairs (ma < mb), 4 steps each:  lane c holds z_a * z_{4 mb + c},  a = 4 ma + i
+//   diagonal blocks, "rotations" of the quad:          r = 0: z_{4m+c}^2
+//                                                      r = 1: z_{4m+c} * z_{4m+(c+1)%4}
+//                                                      r = 2: only 2 distinct products per block, so two blocks
+//                                                             share a step (lanes 0,1: block 2h; lanes 2,3: block 2h+1)
+//   linear terms:                                      lane c holds z_{4m+c}
+// which is exactly D(D+1)/2 + D slots when DQ is even: no padding products, unlike a square 4x4 tiling of the
+// diagonal blocks (which spends 16 slots on 10 distinct products).
+__host__ __device__ constexpr int em_ne_offdiag(int DP) { return 4 * (DP / 4) * (DP / 4 - 1) / 2; }
+__host__ __device__ constexpr int em_ne(int DP) { return em_ne_offdiag(DP) + 2 * (DP / 4) + (DP / 4 + 1) / 2 + DP / 4; }
+// index of the first off-diagonal step of coordinate a = 4 ma + i against block mb > ma
+__host__ __device__ constexpr int em_estep_offdiag(int DP, int a, int mb)
 {
+    const int DQ = DP / 4, ma = a / 4, i = a % 4;
     int n = 0;
-    for (int i = 0; i < a; ++i) n += DP / 4 - i / 4;
-    return n + (m - a / 4);
+    for (int m = 0; m < ma; ++m) n += 4 * (DQ - 1 - m);
+    return n + i * (DQ - 1 - ma) + (mb - ma - 1);
 }
-__host__ __device__ constexpr int em_ne(int DP) { return em_estep_index(DP, DP - 1, DP / 4 - 1) + 1 + DP / 4; }
 // M-step features: 1, z_a, z_a z_b (a <= b), padded to a multiple of 8 rows.
 __host__ __device__ constexpr int em_fm_raw(int DP) { return 1 + DP + DP * (DP + 1) / 2; }
 __host__ __device__ constexpr int em_nm(int DP) { return (em_fm_raw(DP) + 7) / 8; }
@@ -45,7 +67,7 @@ __host__ __device__ constexpr int em_theta_len(int DP, int KP) { return em_ne(DP
 
 constexpr size_t em_smem_bytes(int DP, int KP)
 {
-    return sizeof(double) * (em_theta_len(DP, KP) + 2 * kTile * (DP + 4) + kTile * (KP + 4) + 8 + DP);
+    return sizeof(double) * (em_theta_len(DP, KP) + 2 * kTile * (DP + 4) + kTile * (KP + 4) + 8 + DP + kExpTableSize);
 }
 
 struct EmArgs {
@@ -92,7 +114,7 @@ __device__ __forceinline__ void load_theta_frag(const double* thE, int j, int la
 // MODE 0: fused E+M step.  MODE 1: M-step from given responsibilities.  MODE 2: E-step only,
 // writing responsibilities and labels (the "emit" pass).
 template <int DP, int KP, int MODE>
-__global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 : 2) em_kernel(const EmArgs p)
+__global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? MLB_EM_MINB_SMALL : 2) em_kernel(const EmArgs p)
 {
     constexpr int NT = KP / 8, DQ = DP / 4, NE = em_ne(DP), NM = em_nm(DP);
     constexpr int ZS = DP + 4, RS = KP + 4;
@@ -108,6 +130,7 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 
     double* R = Zb + 2 * kTile * ZS;
     double* wl = R + kTile * RS;
     double* sh = wl + 8;
+    double* etab = sh + DP;   // 2^(j/32) for exp_nonpositive
     __shared__ int s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
@@ -118,6 +141,7 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 
     for (int i = tid; i < 2 * kTile * ZS; i += kEmThreads) Zb[i] = 0.0;
     for (int i = tid; i < kTile * RS; i += kEmThreads) R[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
+    load_exp_table(etab);
 
     // M-step ownership: warp (wm, wn) holds feature tiles wm*MW .. wm*MW+MW-1 x component tiles wn*NW .. +NW-1.
     const int wm = warp / WN, wn = warp % WN;
@@ -176,7 +200,9 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 
 #pragma unroll
                 for (int nt = 0; nt < NW; ++nt) sacc[i][nt][0] = sacc[i][nt][1] = 0.0;
         }
-        double ll_acc = 0.0;
+        // log-likelihood partial: sum_i (max_i + log(sum_i)).  The sums (each in [1, K]) are multiplied up over
+        // kLogBatch tiles and logged once, so the log costs 1/kLogBatch per point (2^(5*2*kLogBatch) at most).
+        double ll_acc = 0.0, ll_prod = 1.0;
 
         load_tile(p_begin, static_cast<int>(min64(kTile, p_end - p_begin)));
         store_tile(Zb, static_cast<int>(min64(kTile, p_end - p_begin)));
@@ -212,31 +238,42 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 
                     zc0[m] = z0[4 * m + c];
                     zc1[m] = z1[4 * m + c];
                 }
-#pragma unroll
-                for (int a = 0; a < DP; ++a) {
-                    const double za0 = z0[a], za1 = z1[a];
-#pragma unroll
-                    for (int m = a / 4; m < DQ; ++m) {
-                        double bf[NT];
-                        load_theta_frag<NT>(thE, em_estep_index(DP, a, m), lane, bf);
-                        const double a0 = za0 * zc0[m], a1 = za1 * zc1[m];
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) {
-                            dmma(acc[0][nt], a0, bf[nt]);
-                            dmma(acc[1][nt], a1, bf[nt]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int m = 0; m < DQ; ++m) {
+                auto estep = [&](int j, double a0, double a1) {
                     double bf[NT];
-                    load_theta_frag<NT>(thE, NE - DQ + m, lane, bf);
+                    load_theta_frag<NT>(thE, j, lane, bf);
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
-                        dmma(acc[0][nt], zc0[m], bf[nt]);
-                        dmma(acc[1][nt], zc1[m], bf[nt]);
+                        dmma(acc[0][nt], a0, bf[nt]);
+                        dmma(acc[1][nt], a1, bf[nt]);
                     }
+                };
+                // off-diagonal block pairs
+#pragma unroll
+                for (int a = 0; a < DP - 4; ++a) {
+                    const double za0 = z0[a], za1 = z1[a];
+#pragma unroll
+                    for (int m = a / 4 + 1; m < DQ; ++m) estep(em_estep_offdiag(DP, a, m), za0 * zc0[m], za1 * zc1[m]);
                 }
+                // diagonal blocks: squares, first rotation, paired second rotation
+                constexpr int J0 = em_ne_offdiag(DP);
+#pragma unroll
+                for (int m = 0; m < DQ; ++m) estep(J0 + m, zc0[m] * zc0[m], zc1[m] * zc1[m]);
+#pragma unroll
+                for (int m = 0; m < DQ; ++m) {
+                    const int o = 4 * m + ((c + 1) & 3);
+                    estep(J0 + DQ + m, zc0[m] * z0[o], zc1[m] * z1[o]);
+                }
+#pragma unroll
+                for (int h = 0; h < (DQ + 1) / 2; ++h) {
+                    const int mx = 2 * h + (c >> 1);                 // lanes 2,3 take the odd block of the pair
+                    const int o = 4 * mx + c, o2 = 4 * mx + ((c + 2) & 3);
+                    const bool live = mx < DQ;                        // DQ odd: the last pair has no second block
+                    const double u0 = live ? z0[o] * z0[o2] : 0.0, u1 = live ? z1[o] * z1[o2] : 0.0;
+                    estep(J0 + 2 * DQ + h, u0, u1);
+                }
+                // linear terms
+#pragma unroll
+                for (int m = 0; m < DQ; ++m) estep(NE - DQ + m, zc0[m], zc1[m]);
                 // ---------------- log-sum-exp over the 4 lanes that share a point
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
@@ -249,14 +286,17 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 
                     double sum = 0.0;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
-                        acc[mt][nt][0] = exp(acc[mt][nt][0] - mx);
-                        acc[mt][nt][1] = exp(acc[mt][nt][1] - mx);
+                        acc[mt][nt][0] = MLB_EM_EXP(acc[mt][nt][0] - mx);
+                        acc[mt][nt][1] = MLB_EM_EXP(acc[mt][nt][1] - mx);
                         sum += acc[mt][nt][0] + acc[mt][nt][1];
                     }
                     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                     const double inv = 1.0 / sum;
-                    if (c == 0 && pl < nvalid) ll_acc += mx + log(sum);
+                    if (c == 0 && pl < nvalid) {
+                        ll_acc += mx;
+                        ll_prod *= sum;
+                    }
                     if (MODE == 0) {
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt)
@@ -305,6 +345,10 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? 3 
                         }
                     }
                 }
+            }
+            if (MODE != 1 && ((t & (kLogBatch - 1)) == kLogBatch - 1 || t + 1 == ntiles)) {
+                ll_acc += log(ll_prod);
+                ll_prod = 1.0;
             }
             if (t + 1 < ntiles) store_tile(Zb + ((t + 1) & 1) * kTile * ZS, nvalid_next);
             __syncthreads();
@@ -478,6 +522,15 @@ __global__ void em_finalize_kernel(const EmFinalizeArgs p)
     }
 }
 
+__global__ void selftest_exp_kernel(const double* x, long long n, double* out)
+{
+    __shared__ double etab[kExpTableSize];
+    load_exp_table(etab);
+    __syncthreads();
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = exp_nonpositive(x[i], etab);
+}
+
 // ---------------------------------------------------------------- dispatch
 
 using EmKernelFn = void (*)(EmArgs);
@@ -629,6 +682,23 @@ static int enqueue_step(mlb_em* em)
 
 extern "C" {
 
+int mlb_selftest_exp(const double* x, int64_t n, double* out)
+{
+    MLB_REQUIRE(x && out && n >= 0, "mlb_selftest_exp: bad argument");
+    if (n == 0) return MLB_OK;
+    MLB_CUDA(cudaSetDevice(0));
+    double *dx = nullptr, *dy = nullptr;
+    MLB_CUDA(cudaMalloc(&dx, sizeof(double) * n));
+    MLB_CUDA(cudaMalloc(&dy, sizeof(double) * n));
+    MLB_CUDA(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    selftest_exp_kernel<<<static_cast<unsigned>((n + 127) / 128), 128>>>(dx, n, dy);
+    MLB_CUDA(cudaGetLastError());
+    MLB_CUDA(cudaMemcpy(out, dy, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    MLB_CUDA(cudaFree(dx));
+    MLB_CUDA(cudaFree(dy));
+    return MLB_OK;
+}
+
 int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
 {
     MLB_REQUIRE(ctx && data && out, "mlb_em_create: null argument");
@@ -643,16 +713,27 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
     em->fn_step = em_kernel_for<0>(DP, KP);
     em->fn_mstep = em_kernel_for<1>(DP, KP);
     em->fn_emit = em_kernel_for<2>(DP, KP);
-    // E-step slots, in the order the kernel enumerates them.
+    // E-step slots, in the order the kernel enumerates them (see em_ne above); (a, b) with a <= b.
     em->feat_e.assign(static_cast<size_t>(em->NE) * 4, make_int2(-1, -1));
-    for (int a = 0; a < DP; ++a)
-        for (int m = a / 4; m < DP / 4; ++m)
+    {
+        const int DQ = DP / 4, J0 = em_ne_offdiag(DP);
+        auto put = [&](int j, int c, int a, int b) { em->feat_e[static_cast<size_t>(j) * 4 + c] = make_int2(std::min(a, b), std::max(a, b)); };
+        for (int a = 0; a < DP - 4; ++a)
+            for (int m = a / 4 + 1; m < DQ; ++m)
+                for (int c = 0; c < 4; ++c) put(em_estep_offdiag(DP, a, m), c, a, 4 * m + c);
+        for (int m = 0; m < DQ; ++m)
             for (int c = 0; c < 4; ++c) {
-                const int b = 4 * m + c;
-                if (b >= a) em->feat_e[em_estep_index(DP, a, m) * 4 + c] = make_int2(a, b);
+                put(J0 + m, c, 4 * m + c, 4 * m + c);
+                put(J0 + DQ + m, c, 4 * m + c, 4 * m + ((c + 1) & 3));
             }
-    for (int m = 0; m < DP / 4; ++m)
-        for (int c = 0; c < 4; ++c) em->feat_e[(em->NE - DP / 4 + m) * 4 + c] = make_int2(4 * m + c, DP);
+        for (int h = 0; h < (DQ + 1) / 2; ++h)
+            for (int c = 0; c < 4; ++c) {
+                const int mx = 2 * h + (c >> 1);
+                if (mx < DQ) put(J0 + 2 * DQ + h, c, 4 * mx + c, 4 * mx + ((c + 2) & 3));
+            }
+        for (int m = 0; m < DQ; ++m)
+            for (int c = 0; c < 4; ++c) em->feat_e[static_cast<size_t>(em->NE - DQ + m) * 4 + c] = make_int2(4 * m + c, DP);
+    }
     // M-step features as offsets into a Z row: [0,DP) coordinates, DP the constant 1, DP+1 a zero.
     em->feat_m.assign(static_cast<size_t>(em->NM) * 8, make_int2(DP + 1, DP + 1));
     {

@@ -25,11 +25,32 @@ void set_error(const char* fmt, ...);
         }                                                                                       \
     } while (0)
 
-#define MLB_NCCL(expr)                                                                          \
+// NCCL is bound at run time (dlopen), never at link time: a process that also hosts PyTorch must end up
+// with ONE libnccl.so.2, and torch ships a newer one than the system's.  nccl() prefers a copy that is
+// already loaded, then $MLB200_NCCL_LIB, then the loader's default libnccl.so.2.  Single-GPU contexts never
+// touch it.  Returns nullptr (with the error text set) when no usable NCCL is found.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*);
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char* (*GetErrorString)(ncclResult_t);
+    ncclResult_t (*GetVersion)(int*);
+};
+const NcclApi* nccl();
+
+#define MLB_NCCL_API(api)                \
+    const ::mlb::NcclApi* api = ::mlb::nccl(); \
+    if (!api) return MLB_ENCCL
+
+#define MLB_NCCL(api, expr)                                                                     \
     do {                                                                                        \
         ncclResult_t mlb_n_ = (expr);                                                           \
         if (mlb_n_ != ncclSuccess) {                                                            \
-            ::mlb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, ncclGetErrorString(mlb_n_)); \
+            ::mlb::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, (api)->GetErrorString(mlb_n_)); \
             return MLB_ENCCL;                                                                   \
         }                                                                                       \
     } while (0)
