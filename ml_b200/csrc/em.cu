@@ -20,6 +20,7 @@
 #include <cstring>
 #include <limits>
 
+#include "em_split.cuh"
 #include "fastmath.cuh"
 #include "internal.h"
 
@@ -558,8 +559,14 @@ struct EmGpu {
     double* stage = nullptr;   // emit / responsibilities staging
     unsigned* stage_labels = nullptr;
     int grid = 0;
+    // split path (general shapes)
+    double* r = nullptr;         // [n_local][KP] responsibilities of the last E-step
+    int2* feat_e_off = nullptr;  // E-step slots as Z-row offsets
+    int grid_e = 0, grid_m = 0;
     KernelTimer timer;
 };
+
+using EmSplitKernelFn = void (*)(EmSplitArgs);
 
 constexpr int kLlRing = 4096;
 constexpr long long kStagePoints = 1 << 20;
@@ -580,6 +587,9 @@ struct mlb_em {
     int64_t launches = 0;
     int64_t steps_done = 0;
     EmKernelFn fn_step = nullptr, fn_mstep = nullptr, fn_emit = nullptr;
+    int path = 1;                // 1: fused E+M kernel (D <= 16, K <= 32); 2: split E / M kernels
+    EmSplitKernelFn fn_split_e = nullptr, fn_split_m = nullptr;
+    size_t smem_split_e = 0, smem_split_m = 0;
 
     double* means(int g) const { return gpus[g].params; }
     double* covs(int g) const { return gpus[g].params + d * k; }
@@ -632,6 +642,62 @@ static int launch_em(mlb_em* em, EmKernelFn fn, const EmArgs& a, int g, int grid
     return MLB_OK;
 }
 
+static EmSplitArgs split_args(const mlb_em* em, int g, const double* theta)
+{
+    const DataShard& sh = em->data->shards[g];
+    const EmGpu& eg = em->gpus[g];
+    EmSplitArgs a{};
+    a.x = sh.x;
+    a.n_local = sh.n();
+    a.d = em->d; a.k = em->k; a.DP = em->DP; a.KP = em->KP;
+    a.shift = sh.shift;
+    a.theta = theta;
+    a.feat_e = eg.feat_e_off;
+    a.feat_m = eg.feat_m;
+    a.ne = em->NE; a.nm = em->NM;
+    a.r = eg.r;
+    a.partials = eg.partials;
+    a.sv = em->SV;
+    a.chunk = em->data->lay.chunk;
+    a.n_chunks = static_cast<int>(sh.n_chunks());
+    a.counter = eg.counter;
+    return a;
+}
+
+// Split path: E kernel (skipped when the responsibilities were supplied by the caller) then M kernel.
+static int launch_split(mlb_em* em, int g, const double* theta, bool run_e, bool timed)
+{
+    Gpu& gpu = em->ctx->gpus[g];
+    EmGpu& eg = em->gpus[g];
+    const EmSplitArgs a = split_args(em, g, theta);
+    if (a.n_chunks == 0) return MLB_OK;
+    if (timed) MLB_TRY(eg.timer.begin(gpu.stream));
+    if (run_e) {
+        MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
+        em->fn_split_e<<<std::min(eg.grid_e, a.n_chunks), kSpThreads, em->smem_split_e, gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        ++em->launches;
+    }
+    const int ngroups = em->KP / (em->NT * 8), nslabs = (em->NM + 4 * kSpMW - 1) / (4 * kSpMW);
+    const long long nitems = static_cast<long long>(a.n_chunks) * nslabs * ngroups;
+    MLB_REQUIRE(nitems < (1ll << 31), "EM split path: too many work items");
+    MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
+    em->fn_split_m<<<static_cast<unsigned>(std::min<long long>(eg.grid_m, nitems)), kSpThreads, em->smem_split_m, gpu.stream>>>(a);
+    MLB_CUDA(cudaGetLastError());
+    ++em->launches;
+    if (timed) MLB_TRY(eg.timer.end(gpu.stream));
+    return MLB_OK;
+}
+
+// One pass over the local points with the E-step image `theta`: statistics into the chunk partials.
+static int launch_pass(mlb_em* em, int g, const double* theta, bool timed)
+{
+    if (em->path == 2) return launch_split(em, g, theta, true, timed);
+    EmArgs a = base_args(em, g);
+    a.theta = theta;
+    return launch_em(em, em->fn_step, a, g, em->gpus[g].grid);
+}
+
 static EmFinalizeArgs finalize_args(const mlb_em* em, int g, bool from_stats, int theta_slot, double* ll_out)
 {
     const EmGpu& eg = em->gpus[g];
@@ -653,6 +719,8 @@ static int launch_finalize(mlb_em* em, int g, bool from_stats, int theta_slot, d
 {
     const EmFinalizeArgs f = finalize_args(em, g, from_stats, theta_slot, ll_out);
     const size_t smem = sizeof(double) * (3 * em->d * em->d + 3 * em->d);
+    if (smem > 48 * 1024)
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em_finalize_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     em_finalize_kernel<<<em->KP, 128, smem, em->ctx->gpus[g].stream>>>(f);
     MLB_CUDA(cudaGetLastError());
     ++em->launches;
@@ -665,7 +733,7 @@ static int enqueue_step(mlb_em* em)
     mlb_ctx* ctx = em->ctx;
     const int ll_slot = static_cast<int>(em->steps_done % kLlRing);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
-        return launch_em(em, em->fn_step, base_args(em, g), g, em->gpus[g].grid);
+        return launch_pass(em, g, em->gpus[g].theta[em->cur], true);
     }));
     std::vector<double*> partials, vsum;
     for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
@@ -705,14 +773,34 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
     MLB_REQUIRE(data->ctx == ctx, "mlb_em_create: data belongs to another context");
     MLB_REQUIRE(k >= 1, "mlb_em_create: number of components must be positive");
     static const int dps[] = {4, 8, 16}, kps[] = {8, 16, 32};
-    const int DP = pad_to(data->d, dps, 3), KP = pad_to(k, kps, 3);
-    MLB_REQUIRE(DP && KP, "mlb_em_create: D=%d, K=%d not supported by this build (D <= 16, K <= 32)", data->d, k);
+    const bool fused = data->d <= 16 && k <= 32;
+    int DP, KP, NT;
+    if (fused) {
+        DP = pad_to(data->d, dps, 3);
+        KP = pad_to(k, kps, 3);
+        NT = KP / 8;
+    } else {
+        // split path: D padded to a multiple of 4, components in groups of 32 (K <= 32) or 64
+        MLB_REQUIRE(data->d <= 64 && k <= 256, "mlb_em_create: D=%d, K=%d not supported by this build (D <= 64, K <= 256)", data->d, k);
+        DP = (data->d + 3) / 4 * 4;
+        const int KG = k > 32 ? 64 : 32;
+        KP = (k + KG - 1) / KG * KG;
+        NT = KG / 8;
+    }
     auto* em = new mlb_em;
     em->ctx = ctx; em->data = data; em->d = data->d; em->k = k;
-    em->DP = DP; em->KP = KP; em->NT = KP / 8; em->NE = em_ne(DP); em->NM = em_nm(DP); em->SV = em_sv(DP, KP);
-    em->fn_step = em_kernel_for<0>(DP, KP);
-    em->fn_mstep = em_kernel_for<1>(DP, KP);
-    em->fn_emit = em_kernel_for<2>(DP, KP);
+    em->path = fused ? 1 : 2;
+    em->DP = DP; em->KP = KP; em->NT = NT; em->NE = em_ne(DP); em->NM = em_nm(DP); em->SV = em_sv(DP, KP);
+    if (fused) {
+        em->fn_step = em_kernel_for<0>(DP, KP);
+        em->fn_mstep = em_kernel_for<1>(DP, KP);
+        em->fn_emit = em_kernel_for<2>(DP, KP);
+    } else {
+        em->fn_split_e = NT == 8 ? em_split_e_kernel<8> : em_split_e_kernel<4>;
+        em->fn_split_m = NT == 8 ? em_split_m_kernel<8> : em_split_m_kernel<4>;
+        em->smem_split_e = em_split_e_smem(NT, DP, KP);
+        em->smem_split_m = em_split_m_smem(NT, DP);
+    }
     // E-step slots, in the order the kernel enumerates them (see em_ne above); (a, b) with a <= b.
     em->feat_e.assign(static_cast<size_t>(em->NE) * 4, make_int2(-1, -1));
     {
@@ -747,7 +835,7 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         EmGpu& eg = em->gpus[g];
         const DataShard& sh = data->shards[g];
-        const size_t theta_len = em_theta_len(DP, KP);
+        const size_t theta_len = static_cast<size_t>(em_theta_len(DP, KP));
         MLB_CUDA(cudaMalloc(&eg.theta[0], sizeof(double) * theta_len));
         MLB_CUDA(cudaMalloc(&eg.theta[1], sizeof(double) * theta_len));
         MLB_CUDA(cudaMalloc(&eg.params, sizeof(double) * em->params_len()));
@@ -760,14 +848,32 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         MLB_CUDA(cudaMemsetAsync(eg.vsum, 0, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(eg.feat_m, em->feat_m.data(), sizeof(int2) * em->feat_m.size(), cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(eg.feat_e, em->feat_e.data(), sizeof(int2) * em->feat_e.size(), cudaMemcpyHostToDevice, gpu.stream));
-        const size_t smem = em_smem_bytes(DP, KP);
-        for (EmKernelFn fn : {em->fn_step, em->fn_mstep, em->fn_emit})
-            MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        int per_sm = 0, sms = 0;
-        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(em->fn_step), kEmThreads, smem));
+        int sms = 0;
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
-        MLB_REQUIRE(per_sm >= 1, "mlb_em_create: EM kernel does not fit on an SM");
-        eg.grid = per_sm * sms;
+        if (em->path == 1) {
+            const size_t smem = em_smem_bytes(DP, KP);
+            for (EmKernelFn fn : {em->fn_step, em->fn_mstep, em->fn_emit})
+                MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            int per_sm = 0;
+            MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(em->fn_step), kEmThreads, smem));
+            MLB_REQUIRE(per_sm >= 1, "mlb_em_create: EM kernel does not fit on an SM");
+            eg.grid = per_sm * sms;
+        } else {
+            std::vector<int2> off(em->feat_e.size());
+            for (size_t i = 0; i < off.size(); ++i) off[i] = em->feat_e[i].x < 0 ? make_int2(DP + 1, DP + 1) : em->feat_e[i];
+            MLB_CUDA(cudaMalloc(&eg.feat_e_off, sizeof(int2) * off.size()));
+            MLB_CUDA(cudaMemcpy(eg.feat_e_off, off.data(), sizeof(int2) * off.size(), cudaMemcpyHostToDevice));
+            MLB_CUDA(cudaMalloc(&eg.r, sizeof(double) * std::max<int64_t>(1, sh.n()) * KP));
+            MLB_CUDA(cudaMemsetAsync(eg.partials, 0, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.stream));
+            MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em->fn_split_e), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(em->smem_split_e)));
+            MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em->fn_split_m), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(em->smem_split_m)));
+            int per_e = 0, per_m = 0;
+            MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_e, reinterpret_cast<const void*>(em->fn_split_e), kSpThreads, em->smem_split_e));
+            MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_m, reinterpret_cast<const void*>(em->fn_split_m), kSpThreads, em->smem_split_m));
+            MLB_REQUIRE(per_e >= 1 && per_m >= 1, "mlb_em_create: EM kernels do not fit on an SM (D=%d, K=%d)", em->d, em->k);
+            eg.grid_e = per_e * sms;
+            eg.grid_m = per_m * sms;
+        }
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
         return MLB_OK;
     });
@@ -787,7 +893,8 @@ int mlb_em_destroy(mlb_em* em)
         for (void* ptr : {static_cast<void*>(eg.theta[0]), static_cast<void*>(eg.theta[1]), static_cast<void*>(eg.params),
                           static_cast<void*>(eg.partials), static_cast<void*>(eg.vsum), static_cast<void*>(eg.ll),
                           static_cast<void*>(eg.feat_m), static_cast<void*>(eg.feat_e), static_cast<void*>(eg.counter),
-                          static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels)})
+                          static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels), static_cast<void*>(eg.r),
+                          static_cast<void*>(eg.feat_e_off)})
             if (ptr) cudaFree(ptr);
     }
     delete em;
@@ -821,7 +928,7 @@ int mlb_em_run_steps(mlb_em* em, int steps, double* log_likelihoods)
         MLB_TRY(enqueue_step(em));
         ++em->steps_done;
     }
-    if (steps > 0) { em->have_step = true; em->last_path = 1; }
+    if (steps > 0) { em->have_step = true; em->last_path = em->path; }
     if (log_likelihoods) {
         Gpu& gpu = em->ctx->gpus[0];
         MLB_CUDA(cudaSetDevice(gpu.device));
@@ -870,13 +977,12 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
     // Uses the spare theta slot and leaves the current parameters untouched.
     const int d = em->d, DP = em->DP, KP = em->KP;
     std::vector<double> theta(em_theta_len(DP, KP), 0.0);
-    for (int kk = 1; kk < KP; ++kk) theta[static_cast<size_t>(em->NE) * em->NT * 32 + kk] = -std::numeric_limits<double>::infinity();
+    for (int kk = 1; kk < KP; ++kk) theta[static_cast<size_t>(em->NE) * (KP / 8) * 32 + kk] = -std::numeric_limits<double>::infinity();
     MLB_TRY(for_each_gpu(em->ctx, [&](int g, Gpu& gpu) -> int {
         MLB_CUDA(cudaMemcpyAsync(em->gpus[g].theta[em->cur ^ 1], theta.data(), sizeof(double) * theta.size(), cudaMemcpyHostToDevice, gpu.stream));
-        EmArgs a = base_args(em, g);
-        a.theta = em->gpus[g].theta[em->cur ^ 1];
-        return launch_em(em, em->fn_step, a, g, em->gpus[g].grid);
+        return launch_pass(em, g, em->gpus[g].theta[em->cur ^ 1], false);
     }));
+    if (em->path == 2) em->have_step = false;   // the pass overwrote the stored responsibilities
     std::vector<double*> partials, vsum;
     for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
     MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV));
@@ -919,9 +1025,18 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
     });
     if (rc == MLB_OK) {
         rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+            const int64_t n = em->data->shards[g].n();
+            if (em->path == 2) {
+                if (n == 0) return MLB_OK;
+                const long long total = static_cast<long long>(n) * em->KP;
+                em_split_import_r_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->gpus[g].stream>>>(dev[g], n, n, em->k, em->KP, em->gpus[g].r);
+                MLB_CUDA(cudaGetLastError());
+                ++em->launches;
+                return launch_split(em, g, em->gpus[g].theta[em->cur], false, false);
+            }
             EmArgs a = base_args(em, g);
             a.r_in = dev[g];
-            a.r_ld = std::max<int64_t>(1, em->data->shards[g].n());  // device copy: local rows only
+            a.r_ld = std::max<int64_t>(1, n);  // device copy: local rows only
             return launch_em(em, em->fn_mstep, a, g, em->gpus[g].grid);
         });
         if (rc == MLB_OK) {
@@ -967,6 +1082,19 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
             if (n <= 0) return MLB_OK;
             any = true;
             EmGpu& eg = em->gpus[g];
+            const int64_t row = lo - begin;
+            if (em->path == 2) {
+                // the responsibilities of the last E-step are resident: transpose them out, argmax for the labels
+                EmSplitArgs a = split_args(em, g, nullptr);
+                a.range_begin = lo - sh.begin;
+                a.range_count = n;
+                a.r_out = resp_out ? eg.stage : nullptr;
+                a.r_out_ld = kStagePoints;
+                a.labels_out = labels_out ? eg.stage_labels : nullptr;
+                em_split_emit_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, gpu.stream>>>(a);
+                MLB_CUDA(cudaGetLastError());
+                ++em->launches;
+            } else {
             EmArgs a = base_args(em, g);
             a.theta = eg.theta[em->cur ^ 1];  // theta_t of the last step
             a.chunk = kTile;
@@ -977,7 +1105,7 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
             a.r_out_ld = kStagePoints;
             a.labels_out = labels_out ? eg.stage_labels : nullptr;
             MLB_TRY(launch_em(em, em->fn_emit, a, g, 8 * kSmCount));
-            const int64_t row = lo - begin;
+            }
             if (resp_out)
                 MLB_CUDA(cudaMemcpy2DAsync(resp_out + row, sizeof(double) * ld, eg.stage, sizeof(double) * kStagePoints, sizeof(double) * n, em->k,
                                            cudaMemcpyDeviceToHost, gpu.stream));

@@ -67,14 +67,23 @@ EM_SHAPES = [
     (4097, 13, 20, 16),
     (777, 1, 2, 17),
 ]
+# general shapes: the split E / M kernels (D > 16 or K > 32)
+EM_SPLIT_SHAPES = [
+    (6000, 24, 8, 31),
+    (9000, 16, 64, 32),
+    (4000, 5, 100, 33),
+    (5003, 20, 33, 34),
+    (6000, 64, 34, 35),
+    (2500, 33, 3, 36),
+]
 
 
-@pytest.mark.parametrize("n,d,k,seed", EM_SHAPES)
+@pytest.mark.parametrize("n,d,k,seed", EM_SHAPES + EM_SPLIT_SHAPES)
 def test_em_fixed_steps_match_oracle(ctx, n, d, k, seed):
     """T iterations from identical initial means: every parameter within 1e-9 relative."""
     data, _, _ = synthetic_gmm(n, d, k, seed=seed, spread=6.0)
     init = np.ascontiguousarray(data[:: n // k][:k].T)  # (D, K): K data points at fixed indices
-    steps = 6
+    steps = 6 if d * d * k <= 20000 else 3
     ref = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=steps,
                         absolute_tolerance=0.0, relative_tolerance=0.0, want_responsibilities=False)
     assert ref.iterations == steps
@@ -88,7 +97,7 @@ def test_em_fixed_steps_match_oracle(ctx, n, d, k, seed):
         assert rel_err(got.covariances[c], ref.covariances[c]) <= RTOL, c
 
 
-@pytest.mark.parametrize("n,d,k,seed", [(10000, 2, 3, 21), (30000, 8, 16, 22), (30000, 16, 32, 23)])
+@pytest.mark.parametrize("n,d,k,seed", [(10000, 2, 3, 21), (30000, 8, 16, 22), (30000, 16, 32, 23), (12000, 24, 12, 24), (12000, 8, 48, 25)])
 def test_em_full_fit_matches_oracle(ctx, n, d, k, seed):
     """Whole fit to convergence: identical iteration count and labels, parameters within 1e-9."""
     data, _, _ = synthetic_gmm(n, d, k, seed=seed, spread=8.0)
@@ -132,10 +141,10 @@ def test_em_sklearn_pin_on_device(ctx):
     assert abs(got.log_likelihood - gm.score(data)) <= 1e-10
 
 
-def test_em_mstep_from_responsibilities(ctx):
+@pytest.mark.parametrize("n,d,k", [(5003, 8, 5), (4001, 20, 6), (3000, 6, 40)])
+def test_em_mstep_from_responsibilities(ctx, n, d, k):
     """maximise_first (EM.cpp:120-125): M-step from one-hot responsibilities equals the oracle's."""
     from ml_b200 import cabi
-    n, d, k = 5003, 8, 5
     data, labels, _ = synthetic_gmm(n, d, k, seed=31)
     resp = np.zeros((n, k))
     resp[np.arange(n), labels] = 1.0
@@ -156,12 +165,13 @@ def test_em_mstep_from_responsibilities(ctx):
     d_data.close()
 
 
-def test_em_is_bitwise_reproducible(ctx):
+@pytest.mark.parametrize("n,d,k", [(50000, 8, 16), (20000, 24, 40)])
+def test_em_is_bitwise_reproducible(ctx, n, d, k):
     """Fixed chunking and fixed-order reductions: two runs give identical bits."""
-    data, _, _ = synthetic_gmm(50000, 8, 16, seed=41)
-    init = np.ascontiguousarray(data[:16].T)
-    a = em_fit_cabi(ctx, data, 16, init, maximum_steps=5, absolute_tolerance=0.0, relative_tolerance=0.0)
-    b = em_fit_cabi(ctx, data, 16, init, maximum_steps=5, absolute_tolerance=0.0, relative_tolerance=0.0)
+    data, _, _ = synthetic_gmm(n, d, k, seed=41)
+    init = np.ascontiguousarray(data[:k].T)
+    a = em_fit_cabi(ctx, data, k, init, maximum_steps=5, absolute_tolerance=0.0, relative_tolerance=0.0)
+    b = em_fit_cabi(ctx, data, k, init, maximum_steps=5, absolute_tolerance=0.0, relative_tolerance=0.0)
     assert a.log_likelihood == b.log_likelihood
     assert np.array_equal(a.means, b.means) and np.array_equal(a.covariances, b.covariances)
 
