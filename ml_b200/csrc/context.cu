@@ -152,20 +152,78 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, Vsha
     }
 }
 
+// Level 1 of the reduction: every run of kReduceGroup consecutive chunks of a virtual shard is summed by one block
+// (same lane scheme as above, so each of the 8 lanes adds exactly 4 chunks), which spreads the read of the
+// partials over thousands of blocks instead of 8 per column tile.  blockIdx.y = group index over all local shards.
+constexpr int kReduceGroup = 32;
+
+__global__ void reduce_groups_kernel(const double* __restrict__ partials, VshardRanges r, int nv, int s, double* __restrict__ out)
+{
+    __shared__ double lanes[8][33];
+    int group = blockIdx.y, v = 0;
+    for (; v < nv; ++v) {
+        const int ng = static_cast<int>((r.hi[v] - r.lo[v] + kReduceGroup - 1) / kReduceGroup);
+        if (group < ng) break;
+        group -= ng;
+    }
+    if (v == nv) return;
+    const int64_t lo = r.lo[v] + static_cast<int64_t>(group) * kReduceGroup;
+    const int64_t hi = min(lo + kReduceGroup, r.hi[v]);
+    const int e = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (e < s) {
+        const int64_t c = lo + 4 * ty;
+        if (c < hi) a0 = partials[c * s + e];
+        if (c + 1 < hi) a1 = partials[(c + 1) * s + e];
+        if (c + 2 < hi) a2 = partials[(c + 2) * s + e];
+        if (c + 3 < hi) a3 = partials[(c + 3) * s + e];
+    }
+    lanes[ty][threadIdx.x] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ty == 0 && e < s) {
+        const int x = threadIdx.x;
+        out[static_cast<int64_t>(blockIdx.y) * s + e] =
+            ((lanes[0][x] + lanes[1][x]) + (lanes[2][x] + lanes[3][x])) + ((lanes[4][x] + lanes[5][x]) + (lanes[6][x] + lanes[7][x]));
+    }
+}
+
 int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s)
 {
     mlb_ctx* ctx = data->ctx;
     const int vpg = ctx->vshards_per_gpu();
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
-        const DataShard& sh = data->shards[g];
-        VshardRanges r;
+        DataShard& sh = data->shards[g];
+        VshardRanges r, rg;
+        int64_t total_groups = 0;
         for (int j = 0; j < vpg; ++j) {
             const int v = gpu.rank * vpg + j;
             r.lo[j] = data->lay.vshard_chunk[v] - sh.chunk_begin;
             r.hi[j] = data->lay.vshard_chunk[v + 1] - sh.chunk_begin;
+            rg.lo[j] = total_groups;
+            total_groups += (r.hi[j] - r.lo[j] + kReduceGroup - 1) / kReduceGroup;
+            rg.hi[j] = total_groups;
         }
-        dim3 grid((s + 31) / 32, vpg);
-        reduce_partials_kernel<<<grid, dim3(32, 8), 0, gpu.stream>>>(partials[g], r, s, vsum[g] + static_cast<int64_t>(gpu.rank) * vpg * s);
+        double* out = vsum[g] + static_cast<int64_t>(gpu.rank) * vpg * s;
+        if (data->lay.n_chunks <= 2 * kReduceGroup * kVirtualShards) {
+            // few chunks: one level.  (The choice depends on N only, never on the GPU count: the two orders differ.)
+            reduce_partials_kernel<<<dim3((s + 31) / 32, vpg), dim3(32, 8), 0, gpu.stream>>>(partials[g], r, s, out);
+            MLB_CUDA(cudaGetLastError());
+            return MLB_OK;
+        }
+        const size_t need = static_cast<size_t>(total_groups) * s;
+        if (sh.reduce_scratch_len < need) {
+            if (sh.reduce_scratch) {
+                MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+                MLB_CUDA(cudaFree(sh.reduce_scratch));
+                sh.reduce_scratch = nullptr;
+                sh.reduce_scratch_len = 0;
+            }
+            MLB_CUDA(cudaMalloc(&sh.reduce_scratch, sizeof(double) * need));
+            sh.reduce_scratch_len = need;
+        }
+        reduce_groups_kernel<<<dim3((s + 31) / 32, static_cast<unsigned>(total_groups)), dim3(32, 8), 0, gpu.stream>>>(partials[g], r, vpg, s, sh.reduce_scratch);
+        MLB_CUDA(cudaGetLastError());
+        reduce_partials_kernel<<<dim3((s + 31) / 32, vpg), dim3(32, 8), 0, gpu.stream>>>(sh.reduce_scratch, rg, s, out);
         MLB_CUDA(cudaGetLastError());
         return MLB_OK;
     }));
@@ -531,6 +589,7 @@ int mlb_data_free(mlb_data* data)
         cudaStreamSynchronize(data->ctx->gpus[g].stream);
         if (data->shards[g].owned && data->shards[g].x) cudaFree(data->shards[g].x);
         if (data->shards[g].shift) cudaFree(data->shards[g].shift);
+        if (data->shards[g].reduce_scratch) cudaFree(data->shards[g].reduce_scratch);
     }
     delete data;
     return MLB_OK;

@@ -111,6 +111,8 @@ struct DataShard {
     int64_t begin = 0, end = 0;           // global point range
     int64_t chunk_begin = 0, chunk_end = 0;  // global chunk range
     double* shift = nullptr;   // d doubles: the global data mean (device copy)
+    double* reduce_scratch = nullptr;  // level-1 group sums of reduce_and_exchange (grown on demand)
+    size_t reduce_scratch_len = 0;
     int64_t n() const { return end - begin; }
     int64_t n_chunks() const { return chunk_end - chunk_begin; }
 };

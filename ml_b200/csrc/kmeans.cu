@@ -49,19 +49,42 @@ __host__ __device__ inline int km_sv(int d, int KP) { return KP * (d + 1) + 8; }
 
 inline size_t km_smem_bytes(int DP, int d, int KP)
 {
-    return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + kKmTile * (DP + 4) + static_cast<size_t>(KP) * (d + 1) + DP + 16) + sizeof(int) * kKmTile;
+    return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + 2 * kKmTile * (DP + 4) + static_cast<size_t>(KP) * (d + 1) + DP + 16) + sizeof(int) * 3 * kKmTile;
 }
 
 // (x - c).squaredNorm() exactly as KMeans.cpp:158 evaluates it (sequential, fused multiply-add).
-__device__ __forceinline__ double exact_distance(const double* x, const double* c, int d)
+// The centroid row comes from global memory (L1/L2): its loads are issued 8 at a time ahead of the dependent FMA chain.
+__device__ __forceinline__ double exact_distance(const double* x, const double* __restrict__ c, int d)
 {
     double s = 0.0;
-    for (int l = 0; l < d; ++l) {
-        const double t = x[l] - c[l];
-        s = fma(t, t, s);
+    for (int l0 = 0; l0 < d; l0 += 8) {
+        double cv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cv[u] = l0 + u < d ? __ldg(c + l0 + u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (l0 + u < d) {
+                const double t = x[l0 + u] - cv[u];
+                s = fma(t, t, s);
+            }
+        }
     }
     return s;
 }
+
+__device__ __forceinline__ void km_cp_async8(void* smem, const void* gmem)
+{
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(gmem));
+}
+__device__ __forceinline__ void km_cp_async4(void* smem, const void* gmem)
+{
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(gmem));
+}
+__device__ __forceinline__ void km_cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void km_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 template <int DP>
 __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p)
@@ -71,17 +94,18 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
     const int KP = p.KP, d = p.d, SD = d + 1;
     double* Bf = sm;                                  // DP * KP
     double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
-    double* X = nrm + KP;                             // kKmTile * XS, raw coordinates (padding columns zero)
-    double* sums = X + kKmTile * XS;                  // KP * (d+1)
+    double* Xb = nrm + KP;                            // 2 x kKmTile * XS, raw coordinates (padding columns zero), double-buffered
+    double* sums = Xb + 2 * kKmTile * XS;             // KP * (d+1)
     double* sh = sums + static_cast<size_t>(KP) * SD; // DP
     double* red = sh + DP;                            // 16
-    int* labs = reinterpret_cast<int*>(red + 16);     // kKmTile
+    int* labs = reinterpret_cast<int*>(red + 16);     // kKmTile: new labels (-1: no point), ~label: ambiguous under the filter
+    unsigned* oldl = reinterpret_cast<unsigned*>(labs + kKmTile);  // 2 x kKmTile: previous labels, double-buffered
     __shared__ int s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
 
     for (int i = tid; i < DP * KP + KP; i += kKmThreads) sm[i] = i < DP * KP ? p.cfrag[i] : p.cnorm[i - DP * KP];
-    for (int i = tid; i < kKmTile * XS; i += kKmThreads) X[i] = 0.0;
+    for (int i = tid; i < 2 * kKmTile * XS; i += kKmThreads) Xb[i] = 0.0;
     for (int i = tid; i < KP * SD; i += kKmThreads) sums[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
     __syncthreads();
@@ -91,6 +115,20 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
     const double u_bound = 8.0 * (d + 4) * 1.1102230246251565e-16;
     const double cmax = *p.cmax;
     const int own_lo = warp * (KP / 8), own_hi = own_lo + KP / 8;   // clusters whose statistics this warp accumulates
+
+    // Asynchronous copy of one tile of points (and their previous labels) into buffer `buf`; rows past the end are zeroed.
+    auto stage = [&](long long tile0, int nvalid, int buf) {
+        double* X = Xb + buf * (kKmTile * XS);
+        const double* xg = p.x + tile0 * d;
+        const int nel = nvalid * d;
+        for (int e = tid; e < kKmTile * d; e += kKmThreads) {
+            const int pt = e / d, dm = e - pt * d;
+            if (e < nel) km_cp_async8(X + pt * XS + dm, xg + e);
+            else X[pt * XS + dm] = 0.0;
+        }
+        if (tid < nvalid) km_cp_async4(oldl + buf * kKmTile + tid, p.labels + tile0 + tid);
+        km_cp_async_commit();
+    };
 
     for (;;) {
         __syncthreads();
@@ -104,18 +142,20 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
         double inertia_acc = 0.0;
         int changed_acc = 0;
 
+        stage(p_begin, static_cast<int>(p_end - p_begin < kKmTile ? p_end - p_begin : kKmTile), 0);
         for (int t = 0; t < ntiles; ++t) {
             const long long tile0 = p_begin + static_cast<long long>(t) * kKmTile;
             const int nvalid = static_cast<int>(p_end - tile0 < kKmTile ? p_end - tile0 : kKmTile);
-            {
-                const double* xg = p.x + tile0 * d;
-                const int nel = nvalid * d;
-                for (int e = tid; e < kKmTile * d; e += kKmThreads) {
-                    const int pt = e / d, dm = e - pt * d;
-                    X[pt * XS + dm] = e < nel ? xg[e] : 0.0;
-                }
+            if (t + 1 < ntiles) {
+                const long long next0 = tile0 + kKmTile;
+                stage(next0, static_cast<int>(p_end - next0 < kKmTile ? p_end - next0 : kKmTile), (t + 1) & 1);
+                km_cp_async_wait<1>();
+            } else {
+                km_cp_async_wait<0>();
             }
             __syncthreads();
+            const double* X = Xb + (t & 1) * (kKmTile * XS);
+            const unsigned* old_labels = oldl + (t & 1) * kKmTile;
 
             // ---------------- filter: scores of this warp's 16 points against all centroids
             const double* x0 = X + (warp * 16 + g) * XS;
@@ -159,7 +199,7 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
                             if (s < best[mt]) { best[mt] = s; bk[mt] = grp * kKmGroup + 8 * nt + 2 * c + e; }
                         }
             }
-            // ---------------- merge over the 4 lanes of a point, then exact refinement
+            // ---------------- merge over the 4 lanes of a point; the filter's verdict goes to shared memory
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 double zz = mt == 0 ? zz0 : zz1;
@@ -174,13 +214,21 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
                     if (ob < best[mt] || (ob == best[mt] && ok < bk[mt])) { best[mt] = ob; bk[mt] = ok; }
                 }
                 const int pl = warp * 16 + mt * 8 + g;
-                if (c == 0 && pl < nvalid) {
-                    const double* xr = X + pl * XS;
+                if (c == 0) {
                     const double root = sqrt(zz) + cmax;
                     const double tau = u_bound * root * root;
-                    int label = bk[mt];
+                    labs[pl] = second[mt] > best[mt] + tau ? bk[mt] : ~bk[mt];
+                }
+            }
+            __syncwarp();
+            // ---------------- exact refinement: lanes 0..15 take one point each of the warp's 16
+            if (lane < 16) {
+                const int pl = warp * 16 + lane;
+                if (pl < nvalid) {
+                    const double* xr = X + pl * XS;
+                    int label = labs[pl];
                     double d2;
-                    if (second[mt] > best[mt] + tau) {
+                    if (label >= 0) {
                         d2 = exact_distance(xr, p.craw + static_cast<long long>(label) * d, d);
                     } else {
                         // ambiguous under the filter's rounding bound: the reference's scan (KMeans.cpp:153-165)
@@ -192,11 +240,10 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
                         }
                     }
                     inertia_acc += d2;
-                    const long long gi = tile0 + pl;
-                    if (p.labels[gi] != static_cast<unsigned>(label)) ++changed_acc;
-                    p.labels[gi] = static_cast<unsigned>(label);
+                    if (old_labels[pl] != static_cast<unsigned>(label)) ++changed_acc;
+                    p.labels[tile0 + pl] = static_cast<unsigned>(label);
                     labs[pl] = label;
-                } else if (c == 0) {
+                } else {
                     labs[pl] = -1;
                 }
             }
