@@ -590,6 +590,7 @@ struct mlb_em {
     int path = 1;                // 1: fused E+M kernel (D <= 16, K <= 32); 2: split E / M kernels
     EmSplitKernelFn fn_split_e = nullptr, fn_split_m = nullptr;
     size_t smem_split_e = 0, smem_split_m = 0;
+    int MW = 4;                  // split M kernel: feature tiles per warp
 
     double* means(int g) const { return gpus[g].params; }
     double* covs(int g) const { return gpus[g].params + d * k; }
@@ -678,7 +679,7 @@ static int launch_split(mlb_em* em, int g, const double* theta, bool run_e, bool
         MLB_CUDA(cudaGetLastError());
         ++em->launches;
     }
-    const int ngroups = em->KP / (em->NT * 8), nslabs = (em->NM + 4 * kSpMW - 1) / (4 * kSpMW);
+    const int ngroups = em->KP / (em->NT * 8), nslabs = (em->NM + 4 * em->MW - 1) / (4 * em->MW);
     const long long nitems = static_cast<long long>(a.n_chunks) * nslabs * ngroups;
     MLB_REQUIRE(nitems < (1ll << 31), "EM split path: too many work items");
     MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
@@ -797,7 +798,14 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         em->fn_emit = em_kernel_for<2>(DP, KP);
     } else {
         em->fn_split_e = NT == 8 ? em_split_e_kernel<8> : em_split_e_kernel<4>;
-        em->fn_split_m = NT == 8 ? em_split_m_kernel<8> : em_split_m_kernel<4>;
+        // feature tiles per warp of the M kernel: the choice that wastes the fewest tile slots (ties: the larger)
+        int best_waste = 1 << 30;
+        for (int mw = 3; mw <= 5; ++mw) {
+            const int slabs = (em->NM + 4 * mw - 1) / (4 * mw), waste = slabs * 4 * mw - em->NM;
+            if (waste <= best_waste) { best_waste = waste; em->MW = mw; }
+        }
+        if (NT == 8) em->fn_split_m = em->MW == 3 ? em_split_m_kernel<8, 3> : em->MW == 4 ? em_split_m_kernel<8, 4> : em_split_m_kernel<8, 5>;
+        else em->fn_split_m = em->MW == 3 ? em_split_m_kernel<4, 3> : em->MW == 4 ? em_split_m_kernel<4, 4> : em_split_m_kernel<4, 5>;
         em->smem_split_e = em_split_e_smem(NT, DP, KP);
         em->smem_split_m = em_split_m_smem(NT, DP);
     }

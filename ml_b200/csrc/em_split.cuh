@@ -24,7 +24,6 @@ namespace mlb {
 constexpr int kSpTile = 64;      // points per tile
 constexpr int kSpThreads = 128;  // 4 warps
 constexpr int kSpJB = 8;         // E-step feature steps per staged Theta block
-constexpr int kSpMW = 4;         // M-step feature tiles (of 8) per warp: a CTA covers 4 * 4 * 8 = 128 features
 constexpr int kSpLogBatch = 8;   // tiles between two log() calls of the log-likelihood partial
 
 struct EmSplitArgs {
@@ -68,9 +67,22 @@ __device__ __forceinline__ void sp_load_z_tile(double* Z, int ZS, const double* 
 {
     const double* xg = x + tile0 * d;
     const int nel = nvalid * d;
-    for (int e = threadIdx.x; e < kSpTile * d; e += kSpThreads) {
-        const int pt = e / d, dm = e - pt * d;
-        Z[pt * ZS + dm] = e < nel ? xg[e] - sh[dm] : 0.0;
+    // 8 loads in flight per thread before the first dependent store
+    for (int e0 = threadIdx.x; e0 < kSpTile * d; e0 += 8 * kSpThreads) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * kSpThreads;
+            v[u] = e < nel ? __ldg(xg + e) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int e = e0 + u * kSpThreads;
+            if (e < kSpTile * d) {
+                const int pt = e / d, dm = e - pt * d;
+                Z[pt * ZS + dm] = e < nel ? v[u] - sh[dm] : 0.0;
+            }
+        }
     }
     if (threadIdx.x < kSpTile) Z[threadIdx.x * ZS + DP] = static_cast<int>(threadIdx.x) < nvalid ? 1.0 : 0.0;
 }
@@ -157,7 +169,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_e_kernel(const EmSplit
                     const double* th = thS + (b & 1) * (kSpJB * NT * 32);
                     const int2* fe = feS + (b & 1) * (kSpJB * 4);
                     const int nj = min(kSpJB, p.ne - b * kSpJB);
-#pragma unroll 2
+#pragma unroll 4
                     for (int jj = 0; jj < nj; ++jj) {
                         const int2 f = fe[jj * 4 + c];
                         const double a0 = z0[f.x] * z0[f.y], a1 = z1[f.x] * z1[f.y];
@@ -230,21 +242,31 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_e_kernel(const EmSplit
     }
 }
 
+constexpr int kSpTileM = 32;     // points per M-step tile (double-buffered with cp.async)
+
 inline size_t em_split_m_smem(int NW, int DP)
 {
-    return sizeof(double) * (kSpTile * (DP + 4) + kSpTile * (8 * NW + 4) + DP);
+    return sizeof(double) * (2 * kSpTileM * (DP + 4) + 2 * kSpTileM * (8 * NW + 4) + DP);
+}
+
+__device__ __forceinline__ void sp_cp_async8(void* smem, const void* gmem)
+{
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem));
 }
 
 // ---------------------------------------------------------------- M kernel
-template <int NW>
-__global__ void __launch_bounds__(kSpThreads, 2) em_split_m_kernel(const EmSplitArgs p)
+// MW = feature tiles (of 8) per warp: a CTA covers 4 * MW * 8 features of one slab; the host picks the MW in {3, 4, 5}
+// that wastes the fewest tile slots for the shape (D = 16: 5, one slab; D = 32: 3; D = 64: 4).
+template <int NW, int MW>
+__global__ void __launch_bounds__(kSpThreads, (NW * MW > 32) ? 1 : 2) em_split_m_kernel(const EmSplitArgs p)
 {
-    constexpr int KG = 8 * NW, RS = KG + 4, MW = kSpMW;
+    constexpr int KG = 8 * NW, RS = KG + 4, TM = kSpTileM;
     extern __shared__ __align__(16) double sm[];
     const int DP = p.DP, KP = p.KP, d = p.d, ZS = DP + 4;
-    double* Z = sm;                     // [64][ZS]
-    double* R = Z + kSpTile * ZS;       // [64][RS]
-    double* sh = R + kSpTile * RS;      // [DP]
+    double* Zb = sm;                        // [2][TM][ZS]
+    double* Rb = Zb + 2 * TM * ZS;          // [2][TM][RS]
+    double* sh = Rb + 2 * TM * RS;          // [DP]
     __shared__ int s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
@@ -252,7 +274,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_m_kernel(const EmSplit
     const int nslabs = (p.nm + 4 * MW - 1) / (4 * MW);
     const int nitems = p.n_chunks * nslabs * ngroups;
 
-    for (int i = tid; i < kSpTile * ZS; i += kSpThreads) Z[i] = 0.0;
+    for (int i = tid; i < 2 * TM * ZS; i += kSpThreads) Zb[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
 
     for (;;) {
@@ -267,7 +289,40 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_m_kernel(const EmSplit
         const int slab = rem / ngroups, cg = rem - slab * ngroups;
         const long long p_begin = static_cast<long long>(chunk) * p.chunk;
         const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
-        const int ntiles = static_cast<int>((p_end - p_begin + kSpTile - 1) / kSpTile);
+        const int ntiles = static_cast<int>((p_end - p_begin + TM - 1) / TM);
+
+        // Asynchronous copy of the raw coordinates and the R rows of one tile; rows past the end are zeroed.
+        auto stage = [&](int t, int buf) {
+            const long long tile0 = p_begin + static_cast<long long>(t) * TM;
+            const int nvalid = static_cast<int>(p_end - tile0 < TM ? p_end - tile0 : TM);
+            double* Z = Zb + buf * (TM * ZS);
+            double* R = Rb + buf * (TM * RS);
+            const double* xg = p.x + tile0 * d;
+            const int nel = nvalid * d;
+            for (int e = tid; e < TM * d; e += kSpThreads) {
+                const int pt = e / d, dm = e - pt * d;
+                if (e < nel) sp_cp_async8(Z + pt * ZS + dm, xg + e);
+                else Z[pt * ZS + dm] = 0.0;
+            }
+            for (int e = tid; e < TM * (KG / 2); e += kSpThreads) {
+                const int pt = e / (KG / 2), q = e - pt * (KG / 2);
+                if (pt < nvalid) sp_cp_async16(R + pt * RS + 2 * q, p.r + (tile0 + pt) * KP + cg * KG + 2 * q);
+                else *reinterpret_cast<double2*>(R + pt * RS + 2 * q) = make_double2(0.0, 0.0);
+            }
+            sp_cp_async_commit();
+        };
+        // Each thread shifts the coordinates it copied itself (visible to it after its own wait), then the block syncs.
+        auto finish = [&](int t, int buf) {
+            const long long tile0 = p_begin + static_cast<long long>(t) * TM;
+            const int nvalid = static_cast<int>(p_end - tile0 < TM ? p_end - tile0 : TM);
+            double* Z = Zb + buf * (TM * ZS);
+            const int nel = nvalid * d;
+            for (int e = tid; e < nel; e += kSpThreads) {
+                const int pt = e / d, dm = e - pt * d;
+                Z[pt * ZS + dm] -= sh[dm];
+            }
+            if (tid < TM) Z[tid * ZS + DP] = tid < nvalid ? 1.0 : 0.0;
+        };
 
         int ia[MW], ib[MW];
 #pragma unroll
@@ -283,19 +338,20 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_m_kernel(const EmSplit
 #pragma unroll
             for (int nt = 0; nt < NW; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
 
+        stage(0, 0);
         for (int t = 0; t < ntiles; ++t) {
-            const long long tile0 = p_begin + static_cast<long long>(t) * kSpTile;
-            const int nvalid = static_cast<int>(p_end - tile0 < kSpTile ? p_end - tile0 : kSpTile);
-            sp_load_z_tile(Z, ZS, p.x, sh, tile0, nvalid, d, DP);
-            for (int e = tid; e < kSpTile * (KG / 2); e += kSpThreads) {
-                const int pt = e / (KG / 2), q = e - pt * (KG / 2);
-                double2 v = make_double2(0.0, 0.0);
-                if (pt < nvalid) v = *reinterpret_cast<const double2*>(p.r + (tile0 + pt) * KP + cg * KG + 2 * q);
-                *reinterpret_cast<double2*>(R + pt * RS + 2 * q) = v;
+            if (t + 1 < ntiles) {
+                stage(t + 1, (t + 1) & 1);
+                sp_cp_async_wait<1>();
+            } else {
+                sp_cp_async_wait<0>();
             }
+            finish(t, t & 1);
             __syncthreads();
+            const double* Z = Zb + (t & 1) * (TM * ZS);
+            const double* R = Rb + (t & 1) * (TM * RS);
 #pragma unroll 2
-            for (int s = 0; s < kSpTile / 4; ++s) {
+            for (int s = 0; s < TM / 4; ++s) {
                 const double* zp = Z + (4 * s + c) * ZS;
                 const double* rp = R + (4 * s + c) * RS + g;
                 double bf[NW];
@@ -308,7 +364,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_m_kernel(const EmSplit
                     for (int nt = 0; nt < NW; ++nt) sp_dmma(acc[i][nt], af, bf[nt]);
                 }
             }
-            __syncthreads();
+            __syncthreads();   // the buffer is refilled by the stage() of the next iteration
         }
 
         double* out = p.partials + static_cast<long long>(chunk) * p.sv;

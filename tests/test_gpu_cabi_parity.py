@@ -73,7 +73,7 @@ EM_SPLIT_SHAPES = [
     (9000, 16, 64, 32),
     (4000, 5, 100, 33),
     (5003, 20, 33, 34),
-    (6000, 64, 34, 35),
+    (10000, 64, 34, 35),
     (2500, 33, 3, 36),
 ]
 
@@ -81,8 +81,13 @@ EM_SPLIT_SHAPES = [
 @pytest.mark.parametrize("n,d,k,seed", EM_SHAPES + EM_SPLIT_SHAPES)
 def test_em_fixed_steps_match_oracle(ctx, n, d, k, seed):
     """T iterations from identical initial means: every parameter within 1e-9 relative."""
-    data, _, _ = synthetic_gmm(n, d, k, seed=seed, spread=6.0)
+    data, _, true_means = synthetic_gmm(n, d, k, seed=seed, spread=6.0)
     init = np.ascontiguousarray(data[:: n // k][:k].T)  # (D, K): K data points at fixed indices
+    if d >= 48:
+        # Few points per component in many dimensions: data-point starts leave components with fewer than D points,
+        # whose covariances are singular (condition number 1e18) and the reference's own arithmetic is noise there.
+        # Starting at the generating means keeps every covariance well conditioned (about 2e2).
+        init = np.ascontiguousarray(true_means.T)
     steps = 6 if d * d * k <= 20000 else 3
     ref = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=steps,
                         absolute_tolerance=0.0, relative_tolerance=0.0, want_responsibilities=False)
