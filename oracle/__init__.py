@@ -15,6 +15,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libmlpp_oracle.so")
+# The reference's own translation units compiled against the Eigen stand-in (oracle/Makefile target `ref`); built in the
+# builder container where /root/reference is mounted, then shipped as a prebuilt file.
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libmlpp_ref.so")
 
 FORGY, RANDOM_PARTITION, KPP, EXPLICIT = 0, 1, 2, 3
 
@@ -117,6 +120,38 @@ def lib():
     return _lib
 
 
+_ref = None
+
+
+def ref_available():
+    """True when oracle/_ref/libmlpp_ref.so (the reference's own sources, see oracle/Makefile) exists."""
+    return os.path.exists(_REF_LIB_PATH)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not ref_available():
+            raise RuntimeError("oracle/_ref/libmlpp_ref.so is not built (run `make -C oracle ref` where /root/reference is mounted)")
+        _ref = ctypes.CDLL(_REF_LIB_PATH)
+        _ref.mlpp_ref_em_fit.restype = ctypes.c_int
+        _ref.mlpp_ref_em_fit.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint, ctypes.POINTER(_EmOptions),
+                                         ctypes.POINTER(_EmResult), ctypes.c_int, _dp, ctypes.c_int64, _dp]
+        _ref.mlpp_ref_kmeans_fit.restype = ctypes.c_int
+        _ref.mlpp_ref_kmeans_fit.argtypes = [_dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint, ctypes.POINTER(_KmOptions),
+                                             ctypes.POINTER(_KmResult), ctypes.c_int, _dp, ctypes.c_int64, _up, _dp]
+        _ref.mlpp_ref_centroids_init.restype = None
+        _ref.mlpp_ref_centroids_init.argtypes = [ctypes.c_int, _dp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint,
+                                                 ctypes.c_uint, ctypes.c_int, _dp]
+        _ref.mlpp_ref_xAx_symmetric.restype = ctypes.c_double
+        _ref.mlpp_ref_xAx_symmetric.argtypes = [_dp, ctypes.c_int64, _dp]
+        _ref.mlpp_ref_xxT.restype = None
+        _ref.mlpp_ref_xxT.argtypes = [_dp, ctypes.c_int64, _dp]
+        _ref.mlpp_ref_add_a_xxT.restype = None
+        _ref.mlpp_ref_add_a_xxT.argtypes = [_dp, ctypes.c_int64, _dp, ctypes.c_double]
+    return _ref
+
+
 def _ptr(a):
     return a.ctypes.data_as(_dp)
 
@@ -135,8 +170,12 @@ class EmFit:
 
 def em_fit(data, k, *, seed=None, absolute_tolerance=1e-8, relative_tolerance=1e-8, maximum_steps=1000,
            means_init=FORGY, resp_init_centroids=FORGY, maximise_first=False, explicit_means=None,
-           want_responsibilities=True):
-    """ml::EM::fit (ML/EM.cpp:91-174) on `data` of shape (N, D), one point per row."""
+           want_responsibilities=True, impl="oracle", count_iterations=True, queries=None):
+    """ml::EM::fit (ML/EM.cpp:91-174) on `data` of shape (N, D), one point per row.
+
+    impl="oracle" runs the restatement (mlpp_oracle.cpp); impl="reference" runs the reference's own ml::EM from
+    oracle/_ref (no per-step clock: `fit_seconds` is the whole fit; no inverse covariances; `queries` (Q, D) are passed
+    to EM::assign_responsibilities after the fit and come back as `query_responsibilities` (Q, K))."""
     data = _check_data(data)
     n, d = data.shape
     opt = _EmOptions()
@@ -171,10 +210,20 @@ def em_fit(data, k, *, seed=None, absolute_tolerance=1e-8, relative_tolerance=1e
     res.responsibilities = _ptr(resp) if resp is not None else None
     res.labels = labels.ctypes.data_as(_up)
     res.step_seconds = _ptr(step_seconds)
-    rc = lib().mlpp_oracle_em_fit(_ptr(data), d, n, d, k, ctypes.byref(opt), ctypes.byref(res))
+    query_out = None
+    if impl == "reference":
+        q = None if queries is None else np.ascontiguousarray(queries, dtype=np.float64)
+        query_out = None if q is None else np.zeros((q.shape[0], k))
+        rc = ref_lib().mlpp_ref_em_fit(_ptr(data), d, n, d, k, ctypes.byref(opt), ctypes.byref(res), int(bool(count_iterations)),
+                                       None if q is None else _ptr(q), 0 if q is None else q.shape[0],
+                                       None if q is None else _ptr(query_out))
+    else:
+        rc = lib().mlpp_oracle_em_fit(_ptr(data), d, n, d, k, ctypes.byref(opt), ctypes.byref(res))
     if rc != 0:
         raise ValueError("EM: invalid arguments")
     out = EmFit()
+    out.query_responsibilities = query_out
+    out.fit_seconds = float(step_seconds[0]) if impl == "reference" else float(np.nansum(step_seconds))
     out.means = means.T.copy()
     out.covariances = covs.transpose(0, 2, 1).copy()  # each block is column-major D x D (symmetric anyway)
     out.inverse_covariances = inv.transpose(0, 2, 1).copy()
@@ -185,7 +234,7 @@ def em_fit(data, k, *, seed=None, absolute_tolerance=1e-8, relative_tolerance=1e
     out.log_likelihood = res.log_likelihood
     out.converged = bool(res.converged)
     out.iterations = int(res.iterations)
-    out.step_seconds = step_seconds[: out.iterations]
+    out.step_seconds = step_seconds[: out.iterations] if impl != "reference" else None
     return out
 
 
@@ -207,8 +256,9 @@ class KMeansFit:
 
 
 def kmeans_fit(data, k, *, seed=None, absolute_tolerance=1e-8, maximum_steps=1000, number_initialisations=1,
-               init=FORGY, explicit_means=None):
-    """ml::Clustering::KMeans::fit (ML/KMeans.cpp:25-114) on `data` of shape (N, D)."""
+               init=FORGY, explicit_means=None, impl="oracle", count_iterations=True, queries=None):
+    """ml::Clustering::KMeans::fit (ML/KMeans.cpp:25-114) on `data` of shape (N, D).  impl as in em_fit; with
+    impl="reference" `queries` (Q, D) go to KMeans::assign_label and come back as `query_labels`, `query_distances`."""
     data = _check_data(data)
     n, d = data.shape
     opt = _KmOptions()
@@ -230,16 +280,27 @@ def kmeans_fit(data, k, *, seed=None, absolute_tolerance=1e-8, maximum_steps=100
     res.centroids = _ptr(centroids)
     res.labels = labels.ctypes.data_as(_up)
     res.step_seconds = _ptr(step_seconds)
-    rc = lib().mlpp_oracle_kmeans_fit(_ptr(data), d, n, d, k, ctypes.byref(opt), ctypes.byref(res))
+    q_labels = q_sq = None
+    if impl == "reference":
+        q = None if queries is None else np.ascontiguousarray(queries, dtype=np.float64)
+        if q is not None:
+            q_labels, q_sq = np.zeros(q.shape[0], dtype=np.uint32), np.zeros(q.shape[0])
+        rc = ref_lib().mlpp_ref_kmeans_fit(_ptr(data), d, n, d, k, ctypes.byref(opt), ctypes.byref(res), int(bool(count_iterations)),
+                                           None if q is None else _ptr(q), 0 if q is None else q.shape[0],
+                                           None if q is None else q_labels.ctypes.data_as(_up), None if q is None else _ptr(q_sq))
+    else:
+        rc = lib().mlpp_oracle_kmeans_fit(_ptr(data), d, n, d, k, ctypes.byref(opt), ctypes.byref(res))
     if rc != 0:
         raise ValueError("KMeans: invalid arguments")
     out = KMeansFit()
+    out.query_labels, out.query_distances = q_labels, q_sq
+    out.fit_seconds = float(step_seconds[0]) if impl == "reference" else float(np.nansum(step_seconds))
     out.centroids = centroids.T.copy()
     out.labels = labels
     out.inertia = res.inertia
     out.converged = bool(res.converged)
     out.iterations = int(res.iterations)
-    out.step_seconds = step_seconds[np.isfinite(step_seconds)]
+    out.step_seconds = step_seconds[np.isfinite(step_seconds)] if impl != "reference" else None
     return out
 
 
@@ -253,33 +314,33 @@ def kmeans_assign_label(centroids, x):
     return int(label), sq.value
 
 
-def centroids_init(kind, data, k, seed=None):
+def centroids_init(kind, data, k, seed=None, impl="oracle"):
     """Forgy / RandomPartition / KPP (ML/Clustering.cpp:16-59).  Returns (D, K)."""
     data = _check_data(data)
     n, d = data.shape
     c = np.zeros((k, d))
-    lib().mlpp_oracle_centroids_init(kind, _ptr(data), d, n, d, k, 0 if seed is None else int(seed),
+    (ref_lib().mlpp_ref_centroids_init if impl == "reference" else lib().mlpp_oracle_centroids_init)(kind, _ptr(data), d, n, d, k, 0 if seed is None else int(seed),
                                      0 if seed is None else 1, _ptr(c))
     return c.T.copy()
 
 
-def xAx_symmetric(A, x):
+def xAx_symmetric(A, x, impl="oracle"):
     A = np.asfortranarray(A, dtype=np.float64)
     x = np.ascontiguousarray(x, dtype=np.float64)
-    return lib().mlpp_oracle_xAx_symmetric(A.ctypes.data_as(_dp), A.shape[0], _ptr(x))
+    return (ref_lib().mlpp_ref_xAx_symmetric if impl == "reference" else lib().mlpp_oracle_xAx_symmetric)(A.ctypes.data_as(_dp), A.shape[0], _ptr(x))
 
 
-def xxT(x):
+def xxT(x, impl="oracle"):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.zeros((x.size, x.size), order="F")
-    lib().mlpp_oracle_xxT(_ptr(x), x.size, out.ctypes.data_as(_dp))
+    (ref_lib().mlpp_ref_xxT if impl == "reference" else lib().mlpp_oracle_xxT)(_ptr(x), x.size, out.ctypes.data_as(_dp))
     return np.array(out)
 
 
-def add_a_xxT(x, dest, a):
+def add_a_xxT(x, dest, a, impl="oracle"):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.asfortranarray(dest, dtype=np.float64).copy(order="F")
-    lib().mlpp_oracle_add_a_xxT(_ptr(x), x.size, out.ctypes.data_as(_dp), a)
+    (ref_lib().mlpp_ref_add_a_xxT if impl == "reference" else lib().mlpp_oracle_add_a_xxT)(_ptr(x), x.size, out.ctypes.data_as(_dp), a)
     return np.array(out)
 
 
