@@ -16,7 +16,9 @@
 // std::discrete_distribution).  Using the very same std:: facilities with the same g++ is the only
 // way to reproduce its PRNG stream bit for bit.  Everything else is plain loops over raw arrays.
 //
-// PARITY STATUS: the reference itself cannot be compiled here (Eigen 3 is neither installed nor
+// PARITY STATUS: pinned bit for bit (with -ffp-contract=off; 1e-13 with release flags) against the reference's own
+// sources compiled with a first-party Eigen stand-in (oracle/_ref, tests/test_oracle_vs_reference.py).  The reference
+// against REAL Eigen cannot be compiled here (Eigen 3 is neither installed nor
 // vendored; SConstruct:24), so the parts of the arithmetic that live inside Eigen are restated from
 // Eigen's documented algorithms with *sequential* summation:
 //     - dense products / reductions (EM.cpp:211, 216, 229, 238, 267-268; squaredNorm call sites),
