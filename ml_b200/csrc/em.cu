@@ -377,6 +377,8 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? ML
     }
 }
 
+#include "em_small.cuh"
+
 // ---------------------------------------------------------------- parameter refresh (replicated on every GPU)
 //
 // One block per (padded) component.  Stage 1 (vsum != nullptr): fixed-tree sum of the 8 virtual
@@ -540,10 +542,12 @@ template <int MODE>
 static EmKernelFn em_kernel_for(int DP, int KP)
 {
 #define MLB_EM_CASE(D_, K_) if (DP == D_ && KP == K_) return em_kernel<D_, K_, MODE>;
-    MLB_EM_CASE(4, 8) MLB_EM_CASE(4, 16) MLB_EM_CASE(4, 32)
-    MLB_EM_CASE(8, 8) MLB_EM_CASE(8, 16) MLB_EM_CASE(8, 32)
+#define MLB_EM_SMALL_CASE(D_, K_) if (DP == D_ && KP == K_) return em_small_kernel<D_, K_, MODE>;
+    MLB_EM_SMALL_CASE(4, 8) MLB_EM_SMALL_CASE(4, 16) MLB_EM_SMALL_CASE(4, 32)
+    MLB_EM_SMALL_CASE(8, 8) MLB_EM_SMALL_CASE(8, 16) MLB_EM_SMALL_CASE(8, 32)
     MLB_EM_CASE(16, 8) MLB_EM_CASE(16, 16) MLB_EM_CASE(16, 32)
 #undef MLB_EM_CASE
+#undef MLB_EM_SMALL_CASE
     return nullptr;
 }
 
@@ -590,6 +594,7 @@ struct mlb_em {
     int path = 1;                // 1: fused E+M kernel (D <= 16, K <= 32); 2: split E / M kernels
     EmSplitKernelFn fn_split_e = nullptr, fn_split_m = nullptr;
     size_t smem_split_e = 0, smem_split_m = 0;
+    size_t smem_fused = 0;       // dynamic shared memory of the fused kernels (em_small_kernel for D <= 8, em_kernel for D = 16)
     int MW = 4;                  // split M kernel: feature tiles per warp
 
     double* means(int g) const { return gpus[g].params; }
@@ -635,7 +640,7 @@ static int launch_em(mlb_em* em, EmKernelFn fn, const EmArgs& a, int g, int grid
     if (a.n_chunks > 0) {
         const bool timed = fn == em->fn_step;
         if (timed) MLB_TRY(em->gpus[g].timer.begin(gpu.stream));
-        fn<<<std::min(grid, a.n_chunks), kEmThreads, em_smem_bytes(em->DP, em->KP), gpu.stream>>>(a);
+        fn<<<std::min(grid, a.n_chunks), kEmThreads, em->smem_fused, gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
         if (timed) MLB_TRY(em->gpus[g].timer.end(gpu.stream));
         ++em->launches;
@@ -796,6 +801,7 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         em->fn_step = em_kernel_for<0>(DP, KP);
         em->fn_mstep = em_kernel_for<1>(DP, KP);
         em->fn_emit = em_kernel_for<2>(DP, KP);
+        em->smem_fused = DP <= 8 ? em_small_smem_bytes(DP, KP) : em_smem_bytes(DP, KP);
     } else {
         em->fn_split_e = NT == 8 ? em_split_e_kernel<8> : em_split_e_kernel<4>;
         // feature tiles per warp of the M kernel: the choice that wastes the fewest tile slots (ties: the larger)
@@ -839,6 +845,15 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         for (int a = 0; a < DP; ++a)
             for (int b = a; b < DP; ++b) em->feat_m[f++] = make_int2(a, b);
     }
+    if (fused && DP <= 8) {
+        // em_small_kernel: the statistics rows are the E-step slots themselves, then the count row (em_small.cuh)
+        for (size_t f = 0; f < em->feat_m.size(); ++f) {
+            int2 ab = make_int2(DP + 1, DP + 1);
+            if (f < em->feat_e.size() && em->feat_e[f].x >= 0) ab = em->feat_e[f];
+            if (static_cast<int>(f) == em_small_count_slot(DP)) ab = make_int2(DP, DP);
+            em->feat_m[f] = ab;
+        }
+    }
     em->gpus.resize(ctx->gpus.size());
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         EmGpu& eg = em->gpus[g];
@@ -859,7 +874,7 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         int sms = 0;
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
         if (em->path == 1) {
-            const size_t smem = em_smem_bytes(DP, KP);
+            const size_t smem = em->smem_fused;
             for (EmKernelFn fn : {em->fn_step, em->fn_mstep, em->fn_emit})
                 MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             int per_sm = 0;
