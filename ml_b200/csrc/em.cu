@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? ML
         for (int r = 0; r < XR; ++r) {
             const int e = tid + kEmThreads * r;
             if (e < kTile * d) {
-                const int pt = (d == DP) ? e / DP : e / d;
+                const int pt = (d == DP) ? e / DP : FastDiv(d).div(e);
                 const int dm = e - pt * d;
                 Z[pt * ZS + dm] = e < nel ? xr[r] - sh[dm] : 0.0;
             }

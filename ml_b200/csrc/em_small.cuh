@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
         for (int r = 0; r < XR; ++r) {
             const int e = lane + 32 * r;
             if (e < kSmallSub * d) {
-                const int pt = (d == DP) ? e / DP : e / d;
+                const int pt = (d == DP) ? e / DP : FastDiv(d).div(e);
                 const int dm = e - pt * d;
                 Z[pt * ZS + dm] = e < nel ? xr[r] - sh[dm] : 0.0;
             }

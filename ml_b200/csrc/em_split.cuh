@@ -67,6 +67,7 @@ __device__ __forceinline__ void sp_load_z_tile(double* Z, int ZS, const double* 
 {
     const double* xg = x + tile0 * d;
     const int nel = nvalid * d;
+    const FastDiv by_d(d);
     // 8 loads in flight per thread before the first dependent store
     for (int e0 = threadIdx.x; e0 < kSpTile * d; e0 += 8 * kSpThreads) {
         double v[8];
@@ -79,7 +80,7 @@ __device__ __forceinline__ void sp_load_z_tile(double* Z, int ZS, const double* 
         for (int u = 0; u < 8; ++u) {
             const int e = e0 + u * kSpThreads;
             if (e < kSpTile * d) {
-                const int pt = e / d, dm = e - pt * d;
+                const int pt = by_d.div(e), dm = e - pt * d;
                 Z[pt * ZS + dm] = e < nel ? v[u] - sh[dm] : 0.0;
             }
         }
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(kSpThreads, (NW * MW > 32) ? 1 : 2) em_split_m
     const int ngroups = KP / KG;
     const int nslabs = (p.nm + 4 * MW - 1) / (4 * MW);
     const int nitems = p.n_chunks * nslabs * ngroups;
+    const FastDiv by_d(d);
 
     for (int i = tid; i < 2 * TM * ZS; i += kSpThreads) Zb[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
@@ -299,10 +301,21 @@ __global__ void __launch_bounds__(kSpThreads, (NW * MW > 32) ? 1 : 2) em_split_m
             double* R = Rb + buf * (TM * RS);
             const double* xg = p.x + tile0 * d;
             const int nel = nvalid * d;
-            for (int e = tid; e < TM * d; e += kSpThreads) {
-                const int pt = e / d, dm = e - pt * d;
-                if (e < nel) sp_cp_async8(Z + pt * ZS + dm, xg + e);
-                else Z[pt * ZS + dm] = 0.0;
+            if ((d & 1) == 0) {
+                // even dimension: rows are 16-byte aligned on both sides, two coordinates per copy
+                const int hd = d >> 1;
+                const FastDiv by_hd(hd);
+                for (int e2 = tid; e2 < TM * hd; e2 += kSpThreads) {
+                    const int pt = by_hd.div(e2), q = e2 - pt * hd;
+                    if (2 * e2 < nel) sp_cp_async16(Z + pt * ZS + 2 * q, xg + 2 * e2);
+                    else *reinterpret_cast<double2*>(Z + pt * ZS + 2 * q) = make_double2(0.0, 0.0);
+                }
+            } else {
+                for (int e = tid; e < TM * d; e += kSpThreads) {
+                    const int pt = by_d.div(e), dm = e - pt * d;
+                    if (e < nel) sp_cp_async8(Z + pt * ZS + dm, xg + e);
+                    else Z[pt * ZS + dm] = 0.0;
+                }
             }
             for (int e = tid; e < TM * (KG / 2); e += kSpThreads) {
                 const int pt = e / (KG / 2), q = e - pt * (KG / 2);
@@ -317,9 +330,20 @@ __global__ void __launch_bounds__(kSpThreads, (NW * MW > 32) ? 1 : 2) em_split_m
             const int nvalid = static_cast<int>(p_end - tile0 < TM ? p_end - tile0 : TM);
             double* Z = Zb + buf * (TM * ZS);
             const int nel = nvalid * d;
-            for (int e = tid; e < nel; e += kSpThreads) {
-                const int pt = e / d, dm = e - pt * d;
-                Z[pt * ZS + dm] -= sh[dm];
+            if ((d & 1) == 0) {
+                const int hd = d >> 1;
+                const FastDiv by_hd(hd);
+                for (int e2 = tid; 2 * e2 < nel; e2 += kSpThreads) {
+                    const int pt = by_hd.div(e2), q = e2 - pt * hd;
+                    double2* cell = reinterpret_cast<double2*>(Z + pt * ZS + 2 * q);
+                    const double2 v = *cell;
+                    *cell = make_double2(v.x - sh[2 * q], v.y - sh[2 * q + 1]);
+                }
+            } else {
+                for (int e = tid; e < nel; e += kSpThreads) {
+                    const int pt = by_d.div(e), dm = e - pt * d;
+                    Z[pt * ZS + dm] -= sh[dm];
+                }
             }
             if (tid < TM) Z[tid * ZS + DP] = tid < nvalid ? 1.0 : 0.0;
         };

@@ -72,6 +72,15 @@ const NcclApi* nccl();
 constexpr int kVirtualShards = MLB_VIRTUAL_SHARDS;
 constexpr int kSmCount = 148;  // B200
 
+// e / d for 0 <= e < 65536 and 1 <= d <= 128 without the ~30-instruction integer division the compiler emits for a
+// run-time divisor: (e + 0.5) / d is at least 0.5 / d away from an integer, far more than the float rounding error.
+struct FastDiv {
+    int d;
+    float inv;
+    __host__ __device__ explicit FastDiv(int divisor) : d(divisor), inv(1.0f / static_cast<float>(divisor)) {}
+    __device__ __forceinline__ int div(int e) const { return __float2int_rz((static_cast<float>(e) + 0.5f) * inv); }
+};
+
 // How the N points are cut up.  A pure function of n_total, so that every GPU count sees the same
 // chunks and therefore the same summation tree (bitwise G-invariance).
 struct Layout {

@@ -20,9 +20,11 @@
 
 namespace mlb {
 
-constexpr int kKmTile = 128;     // points per CTA tile
-constexpr int kKmThreads = 256;  // 8 warps, 16 points each
+constexpr int kKmTile = 64;      // points per CTA tile of the assignment kernel
+constexpr int kKmThreads = 128;  // 4 warps, 16 points each
 constexpr int kKmGroup = 32;     // centroids per accumulator group (4 n-tiles)
+constexpr int kStTile = 128;     // points per CTA tile of the statistics kernel
+constexpr int kStThreads = 256;  // 8 warps, each owning KP / 8 clusters
 
 struct KmArgs {
     const double* x;
@@ -37,7 +39,6 @@ struct KmArgs {
     double* partials;       // [n_chunks][SV]: K x (D+1) sums and counts, inertia, changed
     int chunk, n_chunks;
     unsigned* counter;
-    int accumulate;         // 0: labels / inertia only
 };
 
 __device__ __forceinline__ void km_dmma(double (&acc)[2], double a, double b)
@@ -47,9 +48,13 @@ __device__ __forceinline__ void km_dmma(double (&acc)[2], double a, double b)
 
 __host__ __device__ inline int km_sv(int d, int KP) { return KP * (d + 1) + 8; }
 
-inline size_t km_smem_bytes(int DP, int d, int KP)
+inline size_t km_smem_bytes(int DP, int KP)
 {
-    return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + 2 * kKmTile * (DP + 4) + static_cast<size_t>(KP) * (d + 1) + DP + 16) + sizeof(int) * 3 * kKmTile;
+    return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + 2 * kKmTile * (DP + 4) + DP + 16) + sizeof(int) * 3 * kKmTile;
+}
+inline size_t km_stats_smem_bytes(int d, int KP)
+{
+    return sizeof(double) * (static_cast<size_t>(KP) * (d + 1) + static_cast<size_t>(kStTile) * d + d) + sizeof(int) * kStTile;
 }
 
 // (x - c).squaredNorm() exactly as KMeans.cpp:158 evaluates it (sequential, fused multiply-add).
@@ -77,6 +82,11 @@ __device__ __forceinline__ void km_cp_async8(void* smem, const void* gmem)
     const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem));
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(gmem));
 }
+__device__ __forceinline__ void km_cp_async16(void* smem, const void* gmem)
+{
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gmem));
+}
 __device__ __forceinline__ void km_cp_async4(void* smem, const void* gmem)
 {
     const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(smem));
@@ -86,8 +96,10 @@ __device__ __forceinline__ void km_cp_async_commit() { asm volatile("cp.async.co
 template <int N>
 __device__ __forceinline__ void km_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// ---------------------------------------------------------------- assignment (KMeans.cpp:153-178)
+// Writes the labels and, per chunk, the inertia and the number of changed labels (slots KP*(d+1) and +1 of the partial).
 template <int DP>
-__global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p)
+__global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
 {
     constexpr int DQ = DP / 4, XS = DP + 4;
     extern __shared__ __align__(16) double sm[];
@@ -95,10 +107,9 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
     double* Bf = sm;                                  // DP * KP
     double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
     double* Xb = nrm + KP;                            // 2 x kKmTile * XS, raw coordinates (padding columns zero), double-buffered
-    double* sums = Xb + 2 * kKmTile * XS;             // KP * (d+1)
-    double* sh = sums + static_cast<size_t>(KP) * SD; // DP
+    double* sh = Xb + 2 * kKmTile * XS;               // DP
     double* red = sh + DP;                            // 16
-    int* labs = reinterpret_cast<int*>(red + 16);     // kKmTile: new labels (-1: no point), ~label: ambiguous under the filter
+    int* labs = reinterpret_cast<int*>(red + 16);     // kKmTile: the filter's verdict (~label: ambiguous under its rounding bound)
     unsigned* oldl = reinterpret_cast<unsigned*>(labs + kKmTile);  // 2 x kKmTile: previous labels, double-buffered
     __shared__ int s_next;
 
@@ -106,7 +117,6 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
 
     for (int i = tid; i < DP * KP + KP; i += kKmThreads) sm[i] = i < DP * KP ? p.cfrag[i] : p.cnorm[i - DP * KP];
     for (int i = tid; i < 2 * kKmTile * XS; i += kKmThreads) Xb[i] = 0.0;
-    for (int i = tid; i < KP * SD; i += kKmThreads) sums[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
     __syncthreads();
     double shc[DQ];
@@ -114,17 +124,26 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
     for (int j = 0; j < DQ; ++j) shc[j] = sh[4 * j + c];
     const double u_bound = 8.0 * (d + 4) * 1.1102230246251565e-16;
     const double cmax = *p.cmax;
-    const int own_lo = warp * (KP / 8), own_hi = own_lo + KP / 8;   // clusters whose statistics this warp accumulates
 
     // Asynchronous copy of one tile of points (and their previous labels) into buffer `buf`; rows past the end are zeroed.
+    const FastDiv by_d(d);
     auto stage = [&](long long tile0, int nvalid, int buf) {
         double* X = Xb + buf * (kKmTile * XS);
         const double* xg = p.x + tile0 * d;
         const int nel = nvalid * d;
-        for (int e = tid; e < kKmTile * d; e += kKmThreads) {
-            const int pt = e / d, dm = e - pt * d;
-            if (e < nel) km_cp_async8(X + pt * XS + dm, xg + e);
-            else X[pt * XS + dm] = 0.0;
+        if (d == DP) {
+            // rows are 16-byte aligned on both sides: two coordinates per copy, row index by a shift
+            for (int e2 = tid; e2 < kKmTile * (DP / 2); e2 += kKmThreads) {
+                const int pt = e2 / (DP / 2), q = e2 - pt * (DP / 2);
+                if (2 * e2 < nel) km_cp_async16(X + pt * XS + 2 * q, xg + 2 * e2);
+                else *reinterpret_cast<double2*>(X + pt * XS + 2 * q) = make_double2(0.0, 0.0);
+            }
+        } else {
+            for (int e = tid; e < kKmTile * d; e += kKmThreads) {
+                const int pt = by_d.div(e), dm = e - pt * d;
+                if (e < nel) km_cp_async8(X + pt * XS + dm, xg + e);
+                else X[pt * XS + dm] = 0.0;
+            }
         }
         if (tid < nvalid) km_cp_async4(oldl + buf * kKmTile + tid, p.labels + tile0 + tid);
         km_cp_async_commit();
@@ -194,9 +213,9 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
                     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const double s = acc[mt][nt][e];
-                            second[mt] = fmin(second[mt], fmax(s, best[mt]));
-                            if (s < best[mt]) { best[mt] = s; bk[mt] = grp * kKmGroup + 8 * nt + 2 * c + e; }
+                            const double sc = acc[mt][nt][e];
+                            second[mt] = fmin(second[mt], fmax(sc, best[mt]));
+                            if (sc < best[mt]) { best[mt] = sc; bk[mt] = grp * kKmGroup + 8 * nt + 2 * c + e; }
                         }
             }
             // ---------------- merge over the 4 lanes of a point; the filter's verdict goes to shared memory
@@ -221,61 +240,60 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
                 }
             }
             __syncwarp();
-            // ---------------- exact refinement: lanes 0..15 take one point each of the warp's 16
-            if (lane < 16) {
-                const int pl = warp * 16 + lane;
-                if (pl < nvalid) {
-                    const double* xr = X + pl * XS;
-                    int label = labs[pl];
-                    double d2;
-                    if (label >= 0) {
-                        d2 = exact_distance(xr, p.craw + static_cast<long long>(label) * d, d);
-                    } else {
-                        // ambiguous under the filter's rounding bound: the reference's scan (KMeans.cpp:153-165)
-                        d2 = INFINITY;
-                        label = 0;
-                        for (int kk = 0; kk < p.k; ++kk) {
-                            const double sq = exact_distance(xr, p.craw + static_cast<long long>(kk) * d, d);
-                            if (sq < d2) { d2 = sq; label = kk; }
-                        }
+            // ---------------- exact refinement: two lanes per point.  The reference's sum runs over the dimensions in order
+            // (KMeans.cpp:158); lane 2i takes the first half of the dimensions, hands its partial sum to lane 2i + 1, which
+            // continues the same fused-multiply-add chain over the second half: the same value, with the centroid row's
+            // global loads of both halves in flight together.
+            {
+                const int pl = warp * 16 + (lane >> 1), half = lane & 1;
+                const bool valid = pl < nvalid;
+                const double* xr = X + pl * XS;
+                const int hd = (d + 1) / 2;
+                const int l_lo = half ? hd : 0, l_hi = half ? d : hd;
+                int label = valid ? labs[pl] : 0;
+                const bool ambiguous = label < 0;
+                if (ambiguous) label = ~label;
+                constexpr int HD = DP / 2;
+                double tv[HD];
+                const double* cr = p.craw + static_cast<long long>(label) * d;
+#pragma unroll
+                for (int u = 0; u < HD; ++u) tv[u] = l_lo + u < l_hi ? __ldg(cr + l_lo + u) : 0.0;
+#pragma unroll
+                for (int u = 0; u < HD; ++u) tv[u] = l_lo + u < l_hi ? xr[l_lo + u] - tv[u] : 0.0;
+                double part = 0.0;
+                if (!half) {
+#pragma unroll
+                    for (int u = 0; u < HD; ++u)
+                        if (u < l_hi - l_lo) part = fma(tv[u], tv[u], part);
+                }
+                const double first = __shfl_sync(0xffffffffu, part, lane & ~1);
+                if (half) {
+                    part = first;
+#pragma unroll
+                    for (int u = 0; u < HD; ++u)
+                        if (u < l_hi - l_lo) part = fma(tv[u], tv[u], part);
+                }
+                double d2 = __shfl_sync(0xffffffffu, part, lane | 1);
+                if (valid && ambiguous && !half) {
+                    // ambiguous under the filter's rounding bound: the reference's scan (KMeans.cpp:153-165)
+                    d2 = INFINITY;
+                    label = 0;
+                    for (int kk = 0; kk < p.k; ++kk) {
+                        const double sq = exact_distance(xr, p.craw + static_cast<long long>(kk) * d, d);
+                        if (sq < d2) { d2 = sq; label = kk; }
                     }
+                }
+                if (!half && valid) {
                     inertia_acc += d2;
                     if (old_labels[pl] != static_cast<unsigned>(label)) ++changed_acc;
                     p.labels[tile0 + pl] = static_cast<unsigned>(label);
-                    labs[pl] = label;
-                } else {
-                    labs[pl] = -1;
                 }
             }
-            __syncthreads();
-
-            // ---------------- update statistics: the warp owning a cluster adds its points in index order
-            if (p.accumulate) {
-                for (int base = 0; base < kKmTile; base += 32) {
-                    const int lab = labs[base + lane];
-                    unsigned mask = __ballot_sync(0xffffffffu, lab >= own_lo && lab < own_hi);
-                    while (mask) {
-                        const int b = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int kk = __shfl_sync(0xffffffffu, lab, b);
-                        const double* xr = X + (base + b) * XS;
-                        double* sk = sums + static_cast<size_t>(kk) * SD;
-                        for (int l = lane; l < d; l += 32) sk[l] += xr[l] - sh[l];
-                        if (lane == 0) sk[d] += 1.0;
-                    }
-                }
-            }
-            __syncthreads();
+            __syncthreads();   // the buffers are refilled by the stage() of the next iteration
         }
 
-        // ---------------- flush the chunk's partial statistics
+        // ---------------- the chunk's inertia and changed-label count
         double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
-        if (p.accumulate) {
-            for (int i = tid; i < KP * SD; i += kKmThreads) {
-                out[i] = sums[i];
-                sums[i] = 0.0;
-            }
-        }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, off);
@@ -284,10 +302,78 @@ __global__ void __launch_bounds__(kKmThreads, 1) km_assign_kernel(const KmArgs p
         if (lane == 0) { red[warp] = inertia_acc; red[8 + warp] = static_cast<double>(changed_acc); }
         __syncthreads();
         if (tid == 0) {
-            out[KP * SD] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-            out[KP * SD + 1] = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
+            out[KP * SD] = (red[0] + red[1]) + (red[2] + red[3]);
+            out[KP * SD + 1] = (red[8] + red[9]) + (red[10] + red[11]);
         }
         if (tid >= 2 && tid < 8) out[KP * SD + tid] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- update statistics (KMeans.cpp:180-192)
+// Per chunk and cluster: the count and the sum of z = x - shift over the chunk's points carrying that label.  The warp
+// that owns a cluster adds its points in index order into shared memory: no floating-point atomics, bitwise
+// reproducible.  A separate kernel (it re-reads the points and the fresh labels, 8D + 4 bytes per point, a few percent
+// of the assignment's time) so that the assignment kernel keeps its shared memory for the centroids and runs several
+// CTAs per SM.
+__global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int KP = p.KP, d = p.d, SD = d + 1;
+    double* sums = sm;                                   // KP * (d + 1)
+    double* X = sums + static_cast<size_t>(KP) * SD;     // kStTile * d, raw coordinates
+    double* sh = X + static_cast<size_t>(kStTile) * d;   // d
+    int* labs = reinterpret_cast<int*>(sh + d);          // kStTile
+    __shared__ int s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int own_lo = warp * (KP / 8), own_hi = own_lo + KP / 8;
+
+    for (int i = tid; i < KP * SD; i += kStThreads) sums[i] = 0.0;
+    if (tid < d) sh[tid] = p.shift[tid];
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = static_cast<int>(atomicAdd(p.counter, 1u));
+        __syncthreads();
+        const int chunk = s_next;
+        if (chunk >= p.n_chunks) break;
+        const long long p_begin = static_cast<long long>(chunk) * p.chunk;
+        const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
+        const int ntiles = static_cast<int>((p_end - p_begin + kStTile - 1) / kStTile);
+        for (int t = 0; t < ntiles; ++t) {
+            const long long tile0 = p_begin + static_cast<long long>(t) * kStTile;
+            const int nvalid = static_cast<int>(p_end - tile0 < kStTile ? p_end - tile0 : kStTile);
+            const double* xg = p.x + tile0 * d;
+            const int nel = nvalid * d;
+            for (int e0 = tid; e0 < nel; e0 += 4 * kStThreads) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = e0 + u * kStThreads < nel ? __ldg(xg + e0 + u * kStThreads) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (e0 + u * kStThreads < nel) X[e0 + u * kStThreads] = v[u];
+            }
+            if (tid < kStTile) labs[tid] = tid < nvalid ? static_cast<int>(p.labels[tile0 + tid]) : -1;
+            __syncthreads();
+            for (int base = 0; base < kStTile; base += 32) {
+                const int lab = labs[base + lane];
+                unsigned mask = __ballot_sync(0xffffffffu, lab >= own_lo && lab < own_hi);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int kk = __shfl_sync(0xffffffffu, lab, b);
+                    const double* xr = X + static_cast<size_t>(base + b) * d;
+                    double* sk = sums + static_cast<size_t>(kk) * SD;
+                    for (int l = lane; l < d; l += 32) sk[l] += xr[l] - sh[l];
+                    if (lane == 0) sk[d] += 1.0;
+                }
+            }
+            __syncthreads();
+        }
+        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        for (int i = tid; i < KP * SD; i += kStThreads) {
+            out[i] = sums[i];
+            sums[i] = 0.0;
+        }
     }
 }
 
@@ -390,7 +476,7 @@ struct KmGpu {
     double* vsum = nullptr;
     double* out = nullptr;
     unsigned* counter = nullptr;
-    int grid = 0;
+    int grid = 0, grid_stats = 0;
     KernelTimer timer;
 };
 
@@ -404,7 +490,7 @@ struct mlb_km {
     int d = 0, k = 0, DP = 0, KP = 0, SV = 0;
     std::vector<KmGpu> gpus;
     KmKernelFn fn = nullptr;
-    size_t smem = 0;
+    size_t smem = 0, smem_stats = 0;
     bool have_centroids = false, have_stats = false;
     int64_t launches = 0;
 };
@@ -440,12 +526,13 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         if (d <= cand) { DP = cand; break; }
     MLB_REQUIRE(DP, "mlb_km_create: D=%d not supported by this build (D <= 64)", d);
     const int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup;
-    const size_t smem = km_smem_bytes(DP, d, KP);
-    MLB_REQUIRE(smem <= 227 * 1024, "mlb_km_create: D=%d, K=%d needs %zu bytes of shared memory (limit 232448)", d, k, smem);
+    const size_t smem = km_smem_bytes(DP, KP), smem_stats = km_stats_smem_bytes(d, KP);
+    MLB_REQUIRE(std::max(smem, smem_stats) <= 227 * 1024, "mlb_km_create: D=%d, K=%d needs %zu bytes of shared memory (limit 232448)", d, k, std::max(smem, smem_stats));
     auto* km = new mlb_km;
     km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->SV = km_sv(d, KP);
     km->fn = km_kernel_for(DP);
     km->smem = smem;
+    km->smem_stats = smem_stats;
     km->gpus.resize(ctx->gpus.size());
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         KmGpu& kg = km->gpus[g];
@@ -469,6 +556,10 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means kernel does not fit on an SM");
         kg.grid = per_sm * sms;
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km_stats_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stats)));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km_stats_kernel), kStThreads, smem_stats));
+        MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means statistics kernel does not fit on an SM");
+        kg.grid_stats = per_sm * sms;
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
         return MLB_OK;
     });
@@ -532,14 +623,17 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
         a.shift = sh.shift; a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
         a.labels = kg.labels; a.partials = kg.partials;
         a.chunk = km->data->lay.chunk; a.n_chunks = static_cast<int>(sh.n_chunks());
-        a.counter = kg.counter; a.accumulate = 1;
+        a.counter = kg.counter;
         MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
         if (a.n_chunks > 0) {
             MLB_TRY(kg.timer.begin(gpu.stream));
             km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
             MLB_CUDA(cudaGetLastError());
+            MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+            km_stats_kernel<<<std::min(kg.grid_stats, a.n_chunks), kStThreads, km->smem_stats, gpu.stream>>>(a);
+            MLB_CUDA(cudaGetLastError());
             MLB_TRY(kg.timer.end(gpu.stream));
-            ++km->launches;
+            km->launches += 2;
         }
         return MLB_OK;
     }));
