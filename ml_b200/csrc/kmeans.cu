@@ -188,15 +188,27 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
                 zz0 = fma(z0[j], z0[j], zz0);
                 zz1 = fma(z1[j], z1[j], zz1);
             }
-            double best[2] = {INFINITY, INFINITY}, second[2] = {INFINITY, INFINITY};
+            zz0 += __shfl_xor_sync(0xffffffffu, zz0, 1);
+            zz0 += __shfl_xor_sync(0xffffffffu, zz0, 2);
+            zz1 += __shfl_xor_sync(0xffffffffu, zz1, 1);
+            zz1 += __shfl_xor_sync(0xffffffffu, zz1, 2);
+            // Best / second-best tracking on 32-bit keys.  The accumulators start at |c'|^2 + |z|^2, so a score IS the squared
+            // distance (>= 0 up to rounding) and the high word of the double, read as an integer, orders like the value
+            // with 20 mantissa bits: three integer min/max, a compare and a select per score instead of IEEE fmin/fmax
+            // chains.  What the truncation (and FP64 rounding) cannot separate is sent to the exact scan below.
+            const double zz[2] = {zz0, zz1};
+            int bestk[2] = {0x7fffffff, 0x7fffffff}, secondk[2] = {0x7fffffff, 0x7fffffff};
             int bk[2] = {0, 0};
             for (int grp = 0; grp < KP / kKmGroup; ++grp) {
                 double acc[2][4][2];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const double2 nn = *reinterpret_cast<const double2*>(nrm + grp * kKmGroup + 8 * nt + 2 * c);
-                    acc[0][nt][0] = acc[1][nt][0] = nn.x;
-                    acc[0][nt][1] = acc[1][nt][1] = nn.y;
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        acc[mt][nt][0] = nn.x + zz[mt];
+                        acc[mt][nt][1] = nn.y + zz[mt];
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < DQ; ++j) {
@@ -213,30 +225,31 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
                     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const double sc = acc[mt][nt][e];
-                            second[mt] = fmin(second[mt], fmax(sc, best[mt]));
-                            if (sc < best[mt]) { best[mt] = sc; bk[mt] = grp * kKmGroup + 8 * nt + 2 * c + e; }
+                            const int key = max(__double2hiint(acc[mt][nt][e]), 0);
+                            secondk[mt] = min(secondk[mt], max(key, bestk[mt]));
+                            if (key < bestk[mt]) bk[mt] = grp * kKmGroup + 8 * nt + 2 * c + e;
+                            bestk[mt] = min(bestk[mt], key);
                         }
             }
             // ---------------- merge over the 4 lanes of a point; the filter's verdict goes to shared memory
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                double zz = mt == 0 ? zz0 : zz1;
-                zz += __shfl_xor_sync(0xffffffffu, zz, 1);
-                zz += __shfl_xor_sync(0xffffffffu, zz, 2);
 #pragma unroll
                 for (int off = 1; off <= 2; off <<= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best[mt], off);
-                    const double os = __shfl_xor_sync(0xffffffffu, second[mt], off);
+                    const int ob = __shfl_xor_sync(0xffffffffu, bestk[mt], off);
+                    const int os = __shfl_xor_sync(0xffffffffu, secondk[mt], off);
                     const int ok = __shfl_xor_sync(0xffffffffu, bk[mt], off);
-                    second[mt] = fmin(fmin(second[mt], os), fmax(best[mt], ob));
-                    if (ob < best[mt] || (ob == best[mt] && ok < bk[mt])) { best[mt] = ob; bk[mt] = ok; }
+                    secondk[mt] = min(min(secondk[mt], os), max(bestk[mt], ob));
+                    if (ob < bestk[mt] || (ob == bestk[mt] && ok < bk[mt])) { bestk[mt] = ob; bk[mt] = ok; }
                 }
                 const int pl = warp * 16 + mt * 8 + g;
                 if (c == 0) {
-                    const double root = sqrt(zz) + cmax;
+                    // best score <= best_hi, second score >= second_lo; tau bounds the FP64 rounding of a score
+                    const double best_hi = __hiloint2double(bestk[mt] + 1, 0);
+                    const double second_lo = secondk[mt] == 0x7fffffff ? INFINITY : __hiloint2double(secondk[mt], 0);
+                    const double root = sqrt(zz[mt]) + cmax;
                     const double tau = u_bound * root * root;
-                    labs[pl] = second[mt] > best[mt] + tau ? bk[mt] : ~bk[mt];
+                    labs[pl] = second_lo > best_hi + tau ? bk[mt] : ~bk[mt];
                 }
             }
             __syncwarp();
