@@ -27,12 +27,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# name -> (points per GPU, D, K).  Per-GPU sizes so that --gpus 8 on c3 is the north star's N=100M, D=16, K=32.
+# name -> (kind, points per GPU, D, K).  Per-GPU sizes, so that --gpus 8 is the BASELINE.json configuration:
+# c3 = N=100M D=16 K=32 EM, c4 = N=20M D=64 K=64 EM, c5 = N=100M D=32 K=256 K-means (Lloyd iterations).
 WORKLOADS = {
-    "c2": (10_000_000, 8, 16),
-    "c3": (12_500_000, 16, 32),
+    "c2": ("em", 10_000_000, 8, 16),
+    "c3": ("em", 12_500_000, 16, 32),
+    "c4": ("em", 2_500_000, 64, 64),
+    "c5": ("km", 12_500_000, 32, 256),
 }
 METRIC = "em_point_components_per_second"
+METRIC_KM = "kmeans_point_centroids_per_second"
 UNIT = "Gpoint*comp/s"
 DATA_SEED = 20261018
 # FP64 peak of this pool's B200s measured with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json): a chain of
@@ -44,6 +48,11 @@ FP64_PEAK_TFLOPS_MEASURED = 37.0
 def f_em(d):
     """Algorithmic FP64 flops per point-component pair per iteration."""
     return 2 * d * d + 8 * d + 6
+
+
+def flops_per_iteration(kind, n, d, k):
+    """EM: N K F_EM(D).  K-means: N K (3D + 1) for the assignment + N (2D + 1) for the update."""
+    return n * k * f_em(d) if kind == "em" else n * k * (3 * d + 1) + n * (2 * d + 1)
 
 
 def parse_args():
@@ -72,7 +81,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -109,7 +118,7 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(n_cpu, d, k, steps, warmup):
+def cpu_baseline(n_cpu, d, k, steps, warmup, kind="em"):
     """The reference's CPU algorithm on a bounded sample of the same synthetic mixture, single-threaded as the reference
     is: the oracle port (oracle/mlpp_oracle.cpp), timed by its own per-step clock.
 
@@ -121,39 +130,112 @@ def cpu_baseline(n_cpu, d, k, steps, warmup):
     import numpy as np
     import oracle
     from tests.datasets import synthetic_gmm
-    data, _, _ = synthetic_gmm(n_cpu, d, k, seed=DATA_SEED % 1000, spread=10.0)
+    data, _, _ = synthetic_gmm(n_cpu, d, min(k, 64), seed=DATA_SEED % 1000, spread=10.0)
     init = np.ascontiguousarray(data[:k].T)
-    fit = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=warmup + steps,
-                        absolute_tolerance=0.0, relative_tolerance=0.0, want_responsibilities=False)
+    if kind == "em":
+        fit = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=warmup + steps,
+                            absolute_tolerance=0.0, relative_tolerance=0.0, want_responsibilities=False)
+    else:
+        fit = oracle.kmeans_fit(data, k, init=oracle.EXPLICIT, explicit_means=init, maximum_steps=warmup + steps, absolute_tolerance=0.0)
     secs = fit.step_seconds[warmup:]
     mean = float(np.mean(secs))
+    name = "em_fit" if kind == "em" else "kmeans_fit"
     return {"value": n_cpu * k / mean / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"oracle em_fit, N={n_cpu} D={d} K={k}, {len(secs)} timed iterations after {warmup} warm-up, single thread like the reference",
+            "sample": f"oracle {name}, N={n_cpu} D={d} K={k}, {len(secs)} timed iterations after {warmup} warm-up, single thread like the reference",
             "ms_per_step": mean * 1e3, "host_cores_available": os.cpu_count(),
             "pinned_by": "oracle/_ref (reference sources + Eigen stand-in): bit-identical, tests/test_oracle_vs_reference.py" if oracle.ref_available() else "reference property tests only"}
+
+
+CPU_SAMPLE = {"c2": (200_000, 500_000), "c3": (20_000, 50_000), "c4": (4_000, 6_000), "c5": (20_000, 40_000)}   # (--impl reference, cpu_baseline)
+
+
+def describe(workload, kind, d, k):
+    algo = "ml::EM full-covariance GMM" if kind == "em" else "ml::Clustering::KMeans Lloyd iterations"
+    return f"{workload}: {algo}, D={d}, K={k}"
 
 
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host CPU: the oracle port, which oracle/_ref (the reference's
     own sources compiled against the Eigen stand-in) pins bit for bit; see cpu_baseline for why the port is what is
-    timed.  ml::EM is single-threaded, so is this."""
+    timed.  ml::EM / KMeans are single-threaded, so is this."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_gpu, d, k = WORKLOADS[args.workload]
-    n_cpu = args.cpu_sample or (200_000 if args.workload == "c2" else 20_000)
-    base = cpu_baseline(n_cpu, d, k, args.steps, args.warmup)
+    kind, n_gpu, d, k = WORKLOADS[args.workload]
+    n_cpu = args.cpu_sample or CPU_SAMPLE[args.workload][0]
+    base = cpu_baseline(n_cpu, d, k, args.steps, args.warmup, kind)
     line = {
-        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: ml::EM full-covariance GMM, D={d}, K={k}; CPU sample of N={n_cpu} points (throughput is per point, O(N) per iteration)",
+        "impl": "reference", "metric": METRIC if kind == "em" else METRIC_KM, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": describe(args.workload, kind, d, k) + f"; CPU sample of N={n_cpu} points (throughput is per point, O(N) per iteration)",
                    "points": n_cpu, "dims": d, "components": k},
         "cpu_baseline": {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample", "pinned_by")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+class EmRunner:
+    """EM through the C-ABI: a step is expectation + maximisation + statistics exchange + parameter refresh."""
+    kernel = "fused E+M kernel (em_small_kernel for D <= 8, em_kernel for D = 16) or the split E / M kernels (D > 16 or K > 32)"
+
+    def __init__(self, cabi, np, data, k, init_means):
+        self.np, self.k, self.init = np, k, init_means
+        self.obj = cabi.Em(data, k)
+        cov = self.obj.sample_covariance()
+        self.obj.set_params(init_means, np.repeat(cov[None], k, axis=0), np.full(k, 1.0 / k))
+
+    def run(self, steps, want=False):
+        return self.obj.run_steps(steps, want_ll=want)
+
+    def step_sync(self):
+        return self.obj.step()          # reads the log-likelihood back, as EM::fit's convergence test needs
+
+    def results(self):
+        params = self.obj.get_params()
+        _, labels = self.obj.emit(want_responsibilities=False, want_labels=True)
+        return params, labels
+
+    def result_bytes(self, n_local, d):
+        return n_local * 4 + (d * self.k + self.k * d * d + self.k) * 8
+
+    def param_bytes(self, d):
+        return (d * self.k + self.k * d * d + self.k) * 8 + d * d * 8
+
+
+class KmRunner:
+    """K-means through the C-ABI: a step is assignment_step + update_step (KMeans.cpp:80-109)."""
+    kernel = "km_assign_kernel (DMMA filter + exact refinement) + km_stats_kernel"
+
+    def __init__(self, cabi, np, data, k, init_means):
+        self.np, self.k = np, k
+        self.obj = cabi.Km(data, k)
+        self.obj.set_centroids(init_means)
+        self.last = None
+
+    def run(self, steps, want=False):
+        out = []
+        for _ in range(steps):
+            inertia, changed = self.obj.assign()   # the host needs `changed` for KMeans.cpp:85, so every step reads it back
+            shift = self.obj.update()
+            out.append(inertia)
+        return self.np.array(out)
+
+    def step_sync(self):
+        inertia, _ = self.obj.assign()
+        self.obj.update()
+        return inertia
+
+    def results(self):
+        return self.obj.get_centroids(), self.obj.get_labels()
+
+    def result_bytes(self, n_local, d):
+        return n_local * 4 + d * self.k * 8
+
+    def param_bytes(self, d):
+        return d * self.k * 8
 
 
 def main():
@@ -195,98 +277,99 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    n_per_gpu, d, k = WORKLOADS[args.workload]
+    kind, n_per_gpu, d, k = WORKLOADS[args.workload]
+    Runner = EmRunner if kind == "em" else KmRunner
     n_total = n_per_gpu * world
     ctx = cabi.Context.for_rank(local_rank, rank, world, uid)
-    data = cabi.Data.generate_gmm(ctx, n_total, d, k, seed=DATA_SEED)
+    data = cabi.Data.generate_gmm(ctx, n_total, d, min(k, 64), seed=DATA_SEED)
     _, n_local, _ = data.shape
 
-    # Initial means: K data points at fixed global indices (0..K-1, held by rank 0), identical on every rank.
+    # Initial means / centroids: K data points at fixed global indices (0..K-1, held by rank 0), identical on every rank.
     box = [data.download(0, k) if rank == 0 else None]
     if world > 1:
         dist.broadcast_object_list(box, src=0)
     init_means = np.ascontiguousarray(box[0].T)
 
-    em = cabi.Em(data, k)
-    cov = em.sample_covariance()
-    em.set_params(init_means, np.repeat(cov[None], k, axis=0), np.full(k, 1.0 / k))
+    run = Runner(cabi, np, data, k, init_means)
 
     # ---- value: K steps with the data resident in HBM, CUDA events on the library's stream, max over ranks
-    em.run_steps(args.warmup, want_ll=False)
+    run.run(args.warmup)
     clocks = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         clocks.start()
-    launches0 = em.launch_count
-    em.set_kernel_timing(True)
+    launches0 = run.obj.launch_count
+    run.obj.set_kernel_timing(True)
     barrier()
     ctx.timer_start()
-    lls = em.run_steps(args.steps, want_ll=True)
+    trace = run.run(args.steps, True)
     ms_total = ctx.timer_stop()
     barrier()
-    kernel_ms, kernel_launches = em.kernel_time_ms()
-    em.set_kernel_timing(False)
-    launches = em.launch_count - launches0
+    kernel_ms, kernel_launches = run.obj.kernel_time_ms()
+    run.obj.set_kernel_timing(False)
+    launches = run.obj.launch_count - launches0
     clock_info = clocks.stop() if rank == 0 else None
     ms_total = max_over_ranks(ms_total)
     ms_per_step = ms_total / args.steps
     value = n_total * k / (ms_per_step * 1e-3) / 1e9
     kernel_ms_avg = max_over_ranks(kernel_ms / max(1, kernel_launches))
 
-    # ---- e2e: a whole fit through the C-ABI from pinned host memory (upload, init, K iterations with the
-    # log-likelihood read back every iteration, parameters and labels downloaded), wall clock, max over ranks
+    # ---- e2e: a whole fit through the C-ABI from pinned host memory (upload, init, K iterations with the convergence
+    # scalars read back every iteration, parameters and labels downloaded), wall clock, max over ranks
     e2e = None
     if not args.no_e2e:
         host = torch.empty((n_local, d), dtype=torch.float64, pin_memory=True)
         begin, _ = cabi.shard_range(n_total, world, rank)
         host_np = host.numpy()
         host_np[:] = data.download(begin, n_local)
-        em.close(); data.close()
-        em = data = None
+        run.obj.close(); data.close()
+        run = data = None
 
         def one_fit():
             barrier()
             t0 = time.perf_counter()
             d2 = cabi.Data.upload(ctx, host_np, n_total=n_total)
-            e2 = cabi.Em(d2, k)
-            c2 = e2.sample_covariance()
-            e2.set_params(init_means, np.repeat(c2[None], k, axis=0), np.full(k, 1.0 / k))
-            ll = 0.0
+            r2 = Runner(cabi, np, d2, k, init_means)
+            last = 0.0
             for _ in range(args.steps):
-                ll = e2.step()
-            params = e2.get_params()
-            _, labels = e2.emit(want_responsibilities=False, want_labels=True)
+                last = r2.step_sync()
+            params, labels = r2.results()
             ctx.synchronize()
             barrier()
             dt = time.perf_counter() - t0
-            e2.close(); d2.close()
-            return dt, ll, params, labels
+            bytes_out = r2.result_bytes(n_local, d)
+            bytes_par = r2.param_bytes(d)
+            r2.obj.close(); d2.close()
+            return dt, last, bytes_out, bytes_par
 
         one_fit()  # warm-up (allocator, page faults of the staging paths)
-        dt, ll_e2e, _, labels = one_fit()
+        dt, last_e2e, bytes_out, bytes_par = one_fit()
         dt = max_over_ranks(dt)
-        h2d = n_local * d * 8 + (d * k + k * d * d + k) * 8
-        d2h = n_local * 4 + (d * k + k * d * d + k) * 8 + args.steps * 8 + d * d * 8
+        h2d = n_local * d * 8 + bytes_par
+        d2h = bytes_out + args.steps * 16
         e2e = {"value": n_total * k * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "fit_seconds": dt, "iterations": args.steps,
-               "what": "one whole fit through the C-ABI from pinned host memory: upload of the rank's points, sample covariance, set_params, "
-                       f"{args.steps} iterations each reading back the log-likelihood, parameters and N labels downloaded; bytes are per iteration (totals / iterations)",
-               "log_likelihood": ll_e2e}
-        if args.steps - 1 >= args.warmup:
+               "what": "one whole fit through the C-ABI from pinned host memory: upload of the rank's points, initialisation, "
+                       f"{args.steps} iterations each reading back the convergence scalars, parameters and N labels downloaded; "
+                       "bytes are per iteration (totals / iterations)",
+               "last_scalar": last_e2e}
+        if kind == "em" and args.steps - 1 >= args.warmup:
             # iteration `steps` of the e2e fit is iteration `steps - warmup` of the timed resident run (same data, same start)
-            assert abs(ll_e2e - float(lls[args.steps - 1 - args.warmup])) <= 1e-12 * abs(ll_e2e), "the e2e fit and the resident run disagree"
+            assert abs(last_e2e - float(trace[args.steps - 1 - args.warmup])) <= 1e-12 * abs(last_e2e), "the e2e fit and the resident run disagree"
 
     if rank == 0:
-        flops_per_launch = n_per_gpu * k * f_em(d)
+        flops_per_launch = flops_per_iteration(kind, n_per_gpu, d, k)
         achieved = flops_per_launch / (kernel_ms_avg * 1e-3) / 1e12
         peak = FP64_PEAK_TFLOPS_MEASURED
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file))["hbm_gbs"] if os.path.exists(peaks_file) else 6650.0
+        bytes_per_point = 8 * d if kind == "em" else 8 * d + 4
+        hbm_gbs = n_per_gpu * bytes_per_point / (kernel_ms_avg * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if kind == "em" else METRIC_KM, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: ml::EM full-covariance GMM, N={n_per_gpu} per GPU ({n_total} total), D={d}, K={k}, "
-                                   "initial means = data points 0..K-1, initial covariances = sample covariance",
+            "config": {"workload": describe(args.workload, kind, d, k) + f", N={n_per_gpu} per GPU ({n_total} total), "
+                                   "initial means = data points 0..K-1" + (", initial covariances = sample covariance" if kind == "em" else ""),
                        "points_total": n_total, "points_per_gpu": n_per_gpu, "dims": d, "components": k,
                        "parallelism": f"points sharded over {world} GPU(s), one ncclAllGather of the sufficient statistics per iteration",
                        "l2": f"input is {n_per_gpu * d * 8 / 1e6:.0f} MB per GPU, larger than the 126 MB L2; no flush needed between iterations",
@@ -294,14 +377,14 @@ def main():
             "roofline": {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64); shares the SM's FP64 unit with DFMA",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "measured on this pool with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json has no FP64 figure",
-                         "kernel": "em_kernel<DP,KP,0> (fused E+M)", "kernel_ms_avg": kernel_ms_avg, "kernel_launches_timed": kernel_launches,
-                         "flops_per_launch": flops_per_launch, "flops_per_point_component": f_em(d),
-                         "hbm_achieved_gbs": n_per_gpu * d * 8 / (kernel_ms_avg * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak,
-                         "hbm_frac": n_per_gpu * d * 8 / (kernel_ms_avg * 1e-3) / 1e9 / hbm_peak,
+                         "kernel": Runner.kernel, "kernel_ms_avg": kernel_ms_avg, "kernel_launches_timed": kernel_launches,
+                         "flops_per_launch": flops_per_launch,
+                         "flops_per_point_component": f_em(d) if kind == "em" else 3 * d + 1,
+                         "hbm_achieved_gbs": hbm_gbs, "hbm_peak_gbs": hbm_peak, "hbm_frac": hbm_gbs / hbm_peak,
                          "traffic": None},
             "clocks": clock_info,
             "gpu_launches": launches,
-            "log_likelihood_last": float(lls[-1]),
+            "last_scalar": float(trace[-1]),
         }
         prof = os.path.join(ROOT, "profiles", "traffic_r01.json")
         if os.path.exists(prof):
@@ -309,8 +392,8 @@ def main():
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
-            n_cpu = args.cpu_sample or (500_000 if args.workload == "c2" else 50_000)
-            line["cpu_baseline"] = cpu_baseline(n_cpu, d, k, 3, 1)
+            n_cpu = args.cpu_sample or CPU_SAMPLE[args.workload][1]
+            line["cpu_baseline"] = cpu_baseline(n_cpu, d, k, 3, 1, kind)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
