@@ -69,7 +69,10 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  The sampler is started
+    before the warm-up (nvidia-smi takes a few hundred ms to produce its first line), every line is stamped on arrival,
+    and only the lines that fall inside [mark_begin, mark_end] are reported; a region shorter than the sampling period
+    reports the sample nearest to it."""
 
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -78,6 +81,7 @@ class ClockSampler:
         self.lines = []
         self.proc = None
         self.index = index
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -85,37 +89,52 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            deadline = time.time() + 3.0
+            while not self.lines and time.time() < deadline:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        parsed = []
+        for stamp, line in self.lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+                parsed.append((stamp, float(parts[0]), float(parts[1]), float(parts[2]), [n for n, f in zip(names, parts[3:7]) if f.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, flag in zip(names, parts[3:7]):
-                if flag.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [r for r in parsed if self.t_begin is not None and self.t_begin <= r[0] <= self.t_end]
+        note = "samples inside the timed region"
+        if not inside and parsed and self.t_begin is not None:
+            mid = 0.5 * (self.t_begin + self.t_end)
+            inside = [min(parsed, key=lambda r: abs(r[0] - mid))]
+            note = "timed region shorter than the 20 ms sampling period: nearest sample"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "power_w_max": max((r[3] for r in inside), default=None), "samples": len(inside), "reasons": reasons, "note": note,
+                "timed_region_ms": None if self.t_begin is None else (self.t_end - self.t_begin) * 1e3}
 
 
 def cpu_baseline(n_cpu, d, k, steps, warmup, kind="em"):
@@ -293,18 +312,19 @@ def main():
     run = Runner(cabi, np, data, k, init_means)
 
     # ---- value: K steps with the data resident in HBM, CUDA events on the library's stream, max over ranks
-    run.run(args.warmup)
     clocks = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         clocks.start()
+    run.run(args.warmup)
     launches0 = run.obj.launch_count
     run.obj.set_kernel_timing(True)
     barrier()
+    clocks.mark_begin()
     ctx.timer_start()
     trace = run.run(args.steps, True)
     ms_total = ctx.timer_stop()
     barrier()
+    clocks.mark_end()
     kernel_ms, kernel_launches = run.obj.kernel_time_ms()
     run.obj.set_kernel_timing(False)
     launches = run.obj.launch_count - launches0

@@ -106,12 +106,13 @@ Layout Layout::make(int64_t n_total)
 {
     Layout lay;
     lay.n_total = n_total;
-    // About 6 chunks per SM on each of 8 GPUs, in multiples of the 128-point tile, at most 4096
-    // points: small enough to balance 148 SMs, large enough that the per-chunk flush of partial
-    // statistics is noise.  Depends on n_total ONLY (never on the GPU count).
+    // About 6 chunks per SM on each of 8 GPUs, in multiples of the 128-point tile, at most 2048
+    // points: small enough to balance 148 SMs x up to 4 resident CTAs under the dynamic scheduler (a
+    // 4096-point cap left 4.1 chunks per CTA at 10M points per GPU: a 10 % tail), large enough that the
+    // per-chunk flush of partial statistics is noise.  Depends on n_total ONLY (never on the GPU count).
     int64_t c = n_total / (8 * kSmCount * 6);
     c = (c + 127) / 128 * 128;
-    c = std::max<int64_t>(128, std::min<int64_t>(4096, c));
+    c = std::max<int64_t>(128, std::min<int64_t>(2048, c));
     lay.chunk = static_cast<int>(c);
     lay.n_chunks = (n_total + c - 1) / c;
     for (int v = 0; v <= kVirtualShards; ++v) lay.vshard_chunk[v] = lay.n_chunks * v / kVirtualShards;

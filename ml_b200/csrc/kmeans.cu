@@ -328,8 +328,10 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
 // reproducible.  A separate kernel (it re-reads the points and the fresh labels, 8D + 4 bytes per point, a few percent
 // of the assignment's time) so that the assignment kernel keeps its shared memory for the centroids and runs several
 // CTAs per SM.
+template <int DP>
 __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
 {
+    constexpr int XR = kStTile * DP / kStThreads;   // coordinates of the next tile each thread holds in registers
     extern __shared__ __align__(16) double sm[];
     const int KP = p.KP, d = p.d, SD = d + 1;
     double* sums = sm;                                   // KP * (d + 1)
@@ -352,32 +354,65 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
         const long long p_begin = static_cast<long long>(chunk) * p.chunk;
         const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
         const int ntiles = static_cast<int>((p_end - p_begin + kStTile - 1) / kStTile);
-        for (int t = 0; t < ntiles; ++t) {
+        // The next tile's coordinates and labels travel through registers while the current tile is processed.
+        double xr[XR];
+        int lr = -1;
+        auto prefetch = [&](int t) {
             const long long tile0 = p_begin + static_cast<long long>(t) * kStTile;
             const int nvalid = static_cast<int>(p_end - tile0 < kStTile ? p_end - tile0 : kStTile);
             const double* xg = p.x + tile0 * d;
             const int nel = nvalid * d;
-            for (int e0 = tid; e0 < nel; e0 += 4 * kStThreads) {
-                double v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = e0 + u * kStThreads < nel ? __ldg(xg + e0 + u * kStThreads) : 0.0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (e0 + u * kStThreads < nel) X[e0 + u * kStThreads] = v[u];
+            for (int u = 0; u < XR; ++u) {
+                const int e = tid + u * kStThreads;
+                xr[u] = e < nel ? __ldg(xg + e) : 0.0;
             }
-            if (tid < kStTile) labs[tid] = tid < nvalid ? static_cast<int>(p.labels[tile0 + tid]) : -1;
+            if (tid < kStTile) lr = tid < nvalid ? static_cast<int>(p.labels[tile0 + tid]) : -1;
+        };
+        prefetch(0);
+        for (int t = 0; t < ntiles; ++t) {
+#pragma unroll
+            for (int u = 0; u < XR; ++u) {
+                const int e = tid + u * kStThreads;
+                if (e < kStTile * d) X[e] = xr[u];
+            }
+            if (tid < kStTile) labs[tid] = lr;
             __syncthreads();
+            if (t + 1 < ntiles) prefetch(t + 1);
             for (int base = 0; base < kStTile; base += 32) {
                 const int lab = labs[base + lane];
                 unsigned mask = __ballot_sync(0xffffffffu, lab >= own_lo && lab < own_hi);
+                // Four owned points at a time: when their clusters are all different the four read-add-write chains are
+                // independent and run concurrently; otherwise (two points of one cluster) they run one after the other, so
+                // every cluster still receives its points in index order.
                 while (mask) {
-                    const int b = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int kk = __shfl_sync(0xffffffffu, lab, b);
-                    const double* xr = X + static_cast<size_t>(base + b) * d;
-                    double* sk = sums + static_cast<size_t>(kk) * SD;
-                    for (int l = lane; l < d; l += 32) sk[l] += xr[l] - sh[l];
-                    if (lane == 0) sk[d] += 1.0;
+                    int b[4], kk[4];
+                    int nb = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        b[u] = mask ? __ffs(mask) - 1 : 0;
+                        kk[u] = __shfl_sync(0xffffffffu, lab, b[u]);
+                        if (mask) { ++nb; mask &= mask - 1; }
+                    }
+                    const bool distinct = nb == 4 && kk[0] != kk[1] && kk[0] != kk[2] && kk[0] != kk[3] && kk[1] != kk[2] && kk[1] != kk[3] && kk[2] != kk[3];
+                    if (distinct) {
+                        for (int l = lane; l <= d; l += 32) {
+                            double v[4], cur[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                v[u] = l < d ? X[static_cast<size_t>(base + b[u]) * d + l] - sh[l] : 1.0;   // slot d is the count
+                                cur[u] = sums[static_cast<size_t>(kk[u]) * SD + l];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) sums[static_cast<size_t>(kk[u]) * SD + l] = cur[u] + v[u];
+                        }
+                    } else {
+                        for (int u = 0; u < nb; ++u) {
+                            const double* xr = X + static_cast<size_t>(base + b[u]) * d;
+                            double* sk = sums + static_cast<size_t>(kk[u]) * SD;
+                            for (int l = lane; l <= d; l += 32) sk[l] += l < d ? xr[l] - sh[l] : 1.0;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -478,6 +513,18 @@ static KmKernelFn km_kernel_for(int DP)
     }
 }
 
+static KmKernelFn km_stats_kernel_for(int DP)
+{
+    switch (DP) {
+    case 4: return km_stats_kernel<4>;
+    case 8: return km_stats_kernel<8>;
+    case 16: return km_stats_kernel<16>;
+    case 32: return km_stats_kernel<32>;
+    case 64: return km_stats_kernel<64>;
+    default: return nullptr;
+    }
+}
+
 struct KmGpu {
     double* craw = nullptr;
     double* cold = nullptr;
@@ -502,7 +549,7 @@ struct mlb_km {
     mlb_data* data = nullptr;
     int d = 0, k = 0, DP = 0, KP = 0, SV = 0;
     std::vector<KmGpu> gpus;
-    KmKernelFn fn = nullptr;
+    KmKernelFn fn = nullptr, fn_stats = nullptr;
     size_t smem = 0, smem_stats = 0;
     bool have_centroids = false, have_stats = false;
     int64_t launches = 0;
@@ -544,6 +591,7 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
     auto* km = new mlb_km;
     km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->SV = km_sv(d, KP);
     km->fn = km_kernel_for(DP);
+    km->fn_stats = km_stats_kernel_for(DP);
     km->smem = smem;
     km->smem_stats = smem_stats;
     km->gpus.resize(ctx->gpus.size());
@@ -569,8 +617,8 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means kernel does not fit on an SM");
         kg.grid = per_sm * sms;
-        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km_stats_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stats)));
-        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km_stats_kernel), kStThreads, smem_stats));
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn_stats), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stats)));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn_stats), kStThreads, smem_stats));
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means statistics kernel does not fit on an SM");
         kg.grid_stats = per_sm * sms;
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
@@ -643,7 +691,7 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
             km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
             MLB_CUDA(cudaGetLastError());
             MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-            km_stats_kernel<<<std::min(kg.grid_stats, a.n_chunks), kStThreads, km->smem_stats, gpu.stream>>>(a);
+            km->fn_stats<<<std::min(kg.grid_stats, a.n_chunks), kStThreads, km->smem_stats, gpu.stream>>>(a);
             MLB_CUDA(cudaGetLastError());
             MLB_TRY(kg.timer.end(gpu.stream));
             km->launches += 2;
