@@ -60,6 +60,38 @@ const NcclApi* nccl()
     return &api;
 }
 
+constexpr size_t kBounceBytes = 8u << 20;
+
+int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes)
+{
+    if (bytes == 0) return MLB_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (!gpu.bounce[i]) {
+            MLB_CUDA(cudaMallocHost(&gpu.bounce[i], kBounceBytes));
+            MLB_CUDA(cudaEventCreateWithFlags(&gpu.bounce_ev[i], cudaEventDisableTiming));
+        }
+    }
+    char* out = static_cast<char*>(dst);
+    const char* in = static_cast<const char*>(src_device);
+    size_t prev_off = 0, prev_len = 0;
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += kBounceBytes, ++i) {
+        const size_t len = std::min(kBounceBytes, bytes - off);
+        const int slot = i & 1;
+        MLB_CUDA(cudaMemcpyAsync(gpu.bounce[slot], in + off, len, cudaMemcpyDeviceToHost, gpu.stream));
+        MLB_CUDA(cudaEventRecord(gpu.bounce_ev[slot], gpu.stream));
+        if (i > 0) {
+            MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[slot ^ 1]));
+            std::memcpy(out + prev_off, gpu.bounce[slot ^ 1], prev_len);
+        }
+        prev_off = off;
+        prev_len = len;
+    }
+    MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[(i - 1) & 1]));
+    std::memcpy(out + prev_off, gpu.bounce[(i - 1) & 1], prev_len);
+    return MLB_OK;
+}
+
 int KernelTimer::begin(cudaStream_t stream)
 {
     if (!enabled || used / 2 >= kMaxLaunches) return MLB_OK;
@@ -215,11 +247,11 @@ int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, co
         if (sh.reduce_scratch_len < need) {
             if (sh.reduce_scratch) {
                 MLB_CUDA(cudaStreamSynchronize(gpu.stream));
-                MLB_CUDA(cudaFree(sh.reduce_scratch));
+                MLB_CUDA(cudaFreeAsync(sh.reduce_scratch, gpu.stream));
                 sh.reduce_scratch = nullptr;
                 sh.reduce_scratch_len = 0;
             }
-            MLB_CUDA(cudaMalloc(&sh.reduce_scratch, sizeof(double) * need));
+            MLB_CUDA(cudaMallocAsync(&sh.reduce_scratch, sizeof(double) * need, gpu.stream));
             sh.reduce_scratch_len = need;
         }
         reduce_groups_kernel<<<dim3((s + 31) / 32, static_cast<unsigned>(total_groups)), dim3(32, 8), 0, gpu.stream>>>(partials[g], r, vpg, s, sh.reduce_scratch);
@@ -274,8 +306,8 @@ static int compute_shift(mlb_data* data)
     std::vector<double*> partials(ctx->gpus.size(), nullptr), vsum(ctx->gpus.size(), nullptr);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMalloc(&partials[g], sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * d));
-        MLB_CUDA(cudaMalloc(&vsum[g], sizeof(double) * kVirtualShards * d));
+        MLB_CUDA(cudaMallocAsync(&partials[g], sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * d, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&vsum[g], sizeof(double) * kVirtualShards * d, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(vsum[g], 0, sizeof(double) * kVirtualShards * d, gpu.stream));
         if (sh.n_chunks() > 0) {
             const int threads = std::max(d, 256 / d * d);
@@ -294,11 +326,11 @@ static int compute_shift(mlb_data* data)
     for (int c = 0; c < d; ++c) data->shift[c] = tree8(host.data() + c, d) / static_cast<double>(data->lay.n_total);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMalloc(&sh.shift, sizeof(double) * d));
+        MLB_CUDA(cudaMallocAsync(&sh.shift, sizeof(double) * d, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(sh.shift, data->shift.data(), sizeof(double) * d, cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
-        MLB_CUDA(cudaFree(partials[g]));
-        MLB_CUDA(cudaFree(vsum[g]));
+        MLB_CUDA(cudaFreeAsync(partials[g], gpu.stream));
+        MLB_CUDA(cudaFreeAsync(vsum[g], gpu.stream));
         return MLB_OK;
     }));
     return MLB_OK;
@@ -397,6 +429,13 @@ static int init_gpu(Gpu& gpu)
 {
     MLB_CUDA(cudaSetDevice(gpu.device));
     MLB_CUDA(cudaStreamCreateWithFlags(&gpu.stream, cudaStreamNonBlocking));
+    // All device buffers are stream-ordered allocations from the device's default pool, which keeps freed memory
+    // cached: a second fit reuses the first one's buffers instead of paying cudaMalloc / cudaFree (milliseconds each
+    // at these sizes).  The cache is returned to the driver when the context is destroyed.
+    cudaMemPool_t pool = nullptr;
+    MLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, gpu.device));
+    uint64_t keep = UINT64_MAX;
+    MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     MLB_CUDA(cudaEventCreate(&gpu.ev0));
     MLB_CUDA(cudaEventCreate(&gpu.ev1));
     return MLB_OK;
@@ -498,7 +537,13 @@ int mlb_ctx_destroy(mlb_ctx* ctx)
         if (gpu.comm && nccl()) nccl()->CommDestroy(gpu.comm);
         if (gpu.ev0) cudaEventDestroy(gpu.ev0);
         if (gpu.ev1) cudaEventDestroy(gpu.ev1);
+        for (int i = 0; i < 2; ++i) {
+            if (gpu.bounce[i]) cudaFreeHost(gpu.bounce[i]);
+            if (gpu.bounce_ev[i]) cudaEventDestroy(gpu.bounce_ev[i]);
+        }
         if (gpu.stream) cudaStreamDestroy(gpu.stream);
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, gpu.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
     delete ctx;
     return MLB_OK;
@@ -588,9 +633,9 @@ int mlb_data_free(mlb_data* data)
     for (size_t g = 0; g < data->shards.size(); ++g) {
         cudaSetDevice(data->ctx->gpus[g].device);
         cudaStreamSynchronize(data->ctx->gpus[g].stream);
-        if (data->shards[g].owned && data->shards[g].x) cudaFree(data->shards[g].x);
-        if (data->shards[g].shift) cudaFree(data->shards[g].shift);
-        if (data->shards[g].reduce_scratch) cudaFree(data->shards[g].reduce_scratch);
+        if (data->shards[g].owned && data->shards[g].x) cudaFreeAsync(data->shards[g].x, data->ctx->gpus[g].stream);
+        if (data->shards[g].shift) cudaFreeAsync(data->shards[g].shift, data->ctx->gpus[g].stream);
+        if (data->shards[g].reduce_scratch) cudaFreeAsync(data->shards[g].reduce_scratch, data->ctx->gpus[g].stream);
     }
     delete data;
     return MLB_OK;
@@ -613,7 +658,7 @@ int mlb_data_upload(mlb_ctx* ctx, const double* x, int64_t n, int64_t n_total, i
     }
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMalloc(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d));
+        MLB_CUDA(cudaMallocAsync(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d, gpu.stream));
         if (sh.n() > 0) {
             const double* src = x + (sh.begin - host_begin) * ld;
             if (ld == d) {
@@ -708,11 +753,11 @@ int mlb_data_generate_gmm(mlb_ctx* ctx, int64_t n_total, int d, int k_true, uint
     MLB_TRY(make_shards(ctx, n_total, d, &data));
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMalloc(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d));
+        MLB_CUDA(cudaMallocAsync(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d, gpu.stream));
         double *dm = nullptr, *dl = nullptr, *dw = nullptr;
-        MLB_CUDA(cudaMalloc(&dm, sizeof(double) * means.size()));
-        MLB_CUDA(cudaMalloc(&dl, sizeof(double) * chol.size()));
-        MLB_CUDA(cudaMalloc(&dw, sizeof(double) * cum.size()));
+        MLB_CUDA(cudaMallocAsync(&dm, sizeof(double) * means.size(), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&dl, sizeof(double) * chol.size(), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&dw, sizeof(double) * cum.size(), gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(dm, means.data(), sizeof(double) * means.size(), cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(dl, chol.data(), sizeof(double) * chol.size(), cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(dw, cum.data(), sizeof(double) * cum.size(), cudaMemcpyHostToDevice, gpu.stream));
@@ -722,9 +767,9 @@ int mlb_data_generate_gmm(mlb_ctx* ctx, int64_t n_total, int d, int k_true, uint
             MLB_CUDA(cudaGetLastError());
         }
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
-        MLB_CUDA(cudaFree(dm));
-        MLB_CUDA(cudaFree(dl));
-        MLB_CUDA(cudaFree(dw));
+        MLB_CUDA(cudaFreeAsync(dm, gpu.stream));
+        MLB_CUDA(cudaFreeAsync(dl, gpu.stream));
+        MLB_CUDA(cudaFreeAsync(dw, gpu.stream));
         return MLB_OK;
     });
     if (rc == MLB_OK) rc = compute_shift(data);
@@ -746,9 +791,7 @@ int mlb_data_download(mlb_data* data, int64_t begin, int64_t count, double* out)
         const DataShard& sh = data->shards[g];
         const int64_t lo = std::max(begin, sh.begin), hi = std::min(begin + count, sh.end);
         if (lo < hi) {
-            MLB_CUDA(cudaMemcpyAsync(out + (lo - begin) * d, sh.x + (lo - sh.begin) * d, sizeof(double) * (hi - lo) * d,
-                                     cudaMemcpyDeviceToHost, gpu.stream));
-            MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+            MLB_TRY(staged_d2h(gpu, out + (lo - begin) * d, sh.x + (lo - sh.begin) * d, sizeof(double) * (hi - lo) * d));
             covered += hi - lo;
         }
         return MLB_OK;

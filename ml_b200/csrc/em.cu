@@ -859,15 +859,15 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         EmGpu& eg = em->gpus[g];
         const DataShard& sh = data->shards[g];
         const size_t theta_len = static_cast<size_t>(em_theta_len(DP, KP));
-        MLB_CUDA(cudaMalloc(&eg.theta[0], sizeof(double) * theta_len));
-        MLB_CUDA(cudaMalloc(&eg.theta[1], sizeof(double) * theta_len));
-        MLB_CUDA(cudaMalloc(&eg.params, sizeof(double) * em->params_len()));
-        MLB_CUDA(cudaMalloc(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV));
-        MLB_CUDA(cudaMalloc(&eg.vsum, sizeof(double) * kVirtualShards * em->SV));
-        MLB_CUDA(cudaMalloc(&eg.ll, sizeof(double) * kLlRing));
-        MLB_CUDA(cudaMalloc(&eg.feat_m, sizeof(int2) * em->feat_m.size()));
-        MLB_CUDA(cudaMalloc(&eg.feat_e, sizeof(int2) * em->feat_e.size()));
-        MLB_CUDA(cudaMalloc(&eg.counter, sizeof(unsigned)));
+        MLB_CUDA(cudaMallocAsync(&eg.theta[0], sizeof(double) * theta_len, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.theta[1], sizeof(double) * theta_len, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.params, sizeof(double) * em->params_len(), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.vsum, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.ll, sizeof(double) * kLlRing, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.feat_m, sizeof(int2) * em->feat_m.size(), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.feat_e, sizeof(int2) * em->feat_e.size(), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.counter, sizeof(unsigned), gpu.stream));
         MLB_CUDA(cudaMemsetAsync(eg.vsum, 0, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(eg.feat_m, em->feat_m.data(), sizeof(int2) * em->feat_m.size(), cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(eg.feat_e, em->feat_e.data(), sizeof(int2) * em->feat_e.size(), cudaMemcpyHostToDevice, gpu.stream));
@@ -884,9 +884,10 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         } else {
             std::vector<int2> off(em->feat_e.size());
             for (size_t i = 0; i < off.size(); ++i) off[i] = em->feat_e[i].x < 0 ? make_int2(DP + 1, DP + 1) : em->feat_e[i];
-            MLB_CUDA(cudaMalloc(&eg.feat_e_off, sizeof(int2) * off.size()));
-            MLB_CUDA(cudaMemcpy(eg.feat_e_off, off.data(), sizeof(int2) * off.size(), cudaMemcpyHostToDevice));
-            MLB_CUDA(cudaMalloc(&eg.r, sizeof(double) * std::max<int64_t>(1, sh.n()) * KP));
+            MLB_CUDA(cudaMallocAsync(&eg.feat_e_off, sizeof(int2) * off.size(), gpu.stream));
+            MLB_CUDA(cudaMemcpyAsync(eg.feat_e_off, off.data(), sizeof(int2) * off.size(), cudaMemcpyHostToDevice, gpu.stream));
+            MLB_CUDA(cudaStreamSynchronize(gpu.stream));   // `off` is a local
+            MLB_CUDA(cudaMallocAsync(&eg.r, sizeof(double) * std::max<int64_t>(1, sh.n()) * KP, gpu.stream));
             MLB_CUDA(cudaMemsetAsync(eg.partials, 0, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.stream));
             MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em->fn_split_e), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(em->smem_split_e)));
             MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em->fn_split_m), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(em->smem_split_m)));
@@ -918,7 +919,7 @@ int mlb_em_destroy(mlb_em* em)
                           static_cast<void*>(eg.feat_m), static_cast<void*>(eg.feat_e), static_cast<void*>(eg.counter),
                           static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels), static_cast<void*>(eg.r),
                           static_cast<void*>(eg.feat_e_off)})
-            if (ptr) cudaFree(ptr);
+            if (ptr) cudaFreeAsync(ptr, em->ctx->gpus[g].stream);
     }
     delete em;
     return MLB_OK;
@@ -1040,7 +1041,7 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         const DataShard& sh = em->data->shards[g];
         const int64_t n = std::max<int64_t>(1, sh.n());
-        MLB_CUDA(cudaMalloc(&dev[g], sizeof(double) * n * em->k));
+        MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
         if (sh.n() > 0)
             MLB_CUDA(cudaMemcpy2DAsync(dev[g], sizeof(double) * n, resp + (sh.begin - host_begin), sizeof(double) * ld, sizeof(double) * sh.n(),
                                        em->k, cudaMemcpyHostToDevice, gpu.stream));
@@ -1073,7 +1074,7 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
         if (rc == MLB_OK) rc = mlb_ctx_synchronize(ctx);
     }
     for (size_t g = 0; g < dev.size(); ++g)
-        if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFree(dev[g]); }
+        if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(dev[g], ctx->gpus[g].stream); }
     if (rc == MLB_OK) { em->have_params = true; em->have_step = false; }
     return rc;
 }
@@ -1090,10 +1091,10 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
     for (const DataShard& sh : em->data->shards) covered += std::max<int64_t>(0, std::min(begin + count, sh.end) - std::max(begin, sh.begin));
     MLB_REQUIRE(covered == count, "mlb_em_emit_range: range is not held by this context");
     // Stage by stage: kStagePoints points per GPU at a time through a device buffer.
-    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         EmGpu& eg = em->gpus[g];
-        if (resp_out && !eg.stage) MLB_CUDA(cudaMalloc(&eg.stage, sizeof(double) * kStagePoints * em->k));
-        if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMalloc(&eg.stage_labels, sizeof(unsigned) * kStagePoints));
+        if (resp_out && !eg.stage) MLB_CUDA(cudaMallocAsync(&eg.stage, sizeof(double) * kStagePoints * em->k, gpu.stream));
+        if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMallocAsync(&eg.stage_labels, sizeof(unsigned) * kStagePoints, gpu.stream));
         return MLB_OK;
     }));
     for (int64_t off = 0;; off += kStagePoints) {
@@ -1130,9 +1131,9 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
             MLB_TRY(launch_em(em, em->fn_emit, a, g, 8 * kSmCount));
             }
             if (resp_out)
-                MLB_CUDA(cudaMemcpy2DAsync(resp_out + row, sizeof(double) * ld, eg.stage, sizeof(double) * kStagePoints, sizeof(double) * n, em->k,
-                                           cudaMemcpyDeviceToHost, gpu.stream));
-            if (labels_out) MLB_CUDA(cudaMemcpyAsync(labels_out + row, eg.stage_labels, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, gpu.stream));
+                for (int kk = 0; kk < em->k; ++kk)
+                    MLB_TRY(staged_d2h(gpu, resp_out + row + static_cast<int64_t>(kk) * ld, eg.stage + static_cast<int64_t>(kk) * kStagePoints, sizeof(double) * n));
+            if (labels_out) MLB_TRY(staged_d2h(gpu, labels_out + row, eg.stage_labels, sizeof(unsigned) * n));
             return MLB_OK;
         }));
         MLB_TRY(mlb_ctx_synchronize(ctx));

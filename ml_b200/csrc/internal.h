@@ -100,6 +100,9 @@ struct Gpu {
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;  // null when world == 1
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // pinned bounce buffers for device -> pageable-host copies (staged_d2h)
+    void* bounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
 };
 
 }  // namespace mlb
@@ -154,6 +157,11 @@ int for_each_gpu(mlb_ctx* ctx, F&& body)
 //   vsum[g]:     device, [8][s]; on return every GPU holds all 8 shard vectors.
 // Fixed summation order => deterministic and independent of the GPU count.
 int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s);
+
+// Device -> host copy into memory that is probably pageable (a numpy array, a std::vector): chunks go through two
+// pinned bounce buffers, the DMA of chunk i overlapping the CPU copy-out of chunk i - 1.  A direct cudaMemcpy into
+// pageable memory runs at ~4 GB/s on these boxes; this path is bounded by the CPU copy (~10+ GB/s).  Synchronous.
+int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes);
 
 // Event pairs around the launches of one kernel on one stream (roofline timing for bench.py).
 struct KernelTimer {

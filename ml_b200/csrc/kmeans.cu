@@ -598,16 +598,16 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         KmGpu& kg = km->gpus[g];
         const DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMalloc(&kg.craw, sizeof(double) * d * k));
-        MLB_CUDA(cudaMalloc(&kg.cold, sizeof(double) * d * k));
-        MLB_CUDA(cudaMalloc(&kg.cfrag, sizeof(double) * DP * KP));
-        MLB_CUDA(cudaMalloc(&kg.cnorm, sizeof(double) * KP));
-        MLB_CUDA(cudaMalloc(&kg.cmax, sizeof(double)));
-        MLB_CUDA(cudaMalloc(&kg.labels, sizeof(unsigned) * std::max<int64_t>(1, sh.n())));
-        MLB_CUDA(cudaMalloc(&kg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV));
-        MLB_CUDA(cudaMalloc(&kg.vsum, sizeof(double) * kVirtualShards * km->SV));
-        MLB_CUDA(cudaMalloc(&kg.out, sizeof(double) * 4));
-        MLB_CUDA(cudaMalloc(&kg.counter, sizeof(unsigned)));
+        MLB_CUDA(cudaMallocAsync(&kg.craw, sizeof(double) * d * k, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.cold, sizeof(double) * d * k, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.cfrag, sizeof(double) * DP * KP, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.cnorm, sizeof(double) * KP, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.cmax, sizeof(double), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.labels, sizeof(unsigned) * std::max<int64_t>(1, sh.n()), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.vsum, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.out, sizeof(double) * 4, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.counter, sizeof(unsigned), gpu.stream));
         MLB_CUDA(cudaMemsetAsync(kg.labels, 0, sizeof(unsigned) * std::max<int64_t>(1, sh.n()), gpu.stream));   // labels_.resize(): zeros
         MLB_CUDA(cudaMemsetAsync(kg.vsum, 0, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(kg.cold, 0, sizeof(double) * d * k, gpu.stream));
@@ -640,7 +640,7 @@ int mlb_km_destroy(mlb_km* km)
         for (void* ptr : {static_cast<void*>(kg.craw), static_cast<void*>(kg.cold), static_cast<void*>(kg.cfrag), static_cast<void*>(kg.cnorm),
                           static_cast<void*>(kg.cmax), static_cast<void*>(kg.labels), static_cast<void*>(kg.partials), static_cast<void*>(kg.vsum),
                           static_cast<void*>(kg.out), static_cast<void*>(kg.counter)})
-            if (ptr) cudaFree(ptr);
+            if (ptr) cudaFreeAsync(ptr, km->ctx->gpus[g].stream);
     }
     delete km;
     return MLB_OK;
@@ -747,8 +747,7 @@ int mlb_km_get_labels(mlb_km* km, unsigned int* labels)
     const int64_t host_begin = km->ctx->rank_mode ? km->data->shards[0].begin : 0;
     MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
         const DataShard& sh = km->data->shards[g];
-        if (sh.n() > 0)
-            MLB_CUDA(cudaMemcpyAsync(labels + (sh.begin - host_begin), km->gpus[g].labels, sizeof(unsigned) * sh.n(), cudaMemcpyDeviceToHost, gpu.stream));
+        if (sh.n() > 0) MLB_TRY(staged_d2h(gpu, labels + (sh.begin - host_begin), km->gpus[g].labels, sizeof(unsigned) * sh.n()));
         return MLB_OK;
     }));
     return mlb_ctx_synchronize(km->ctx);
