@@ -400,7 +400,9 @@ struct EmFinalizeArgs {
     double* inv_covs;     // K x (D x D)
     double* sqrt_dets;    // K
     double* theta_out;    // E-step image
-    double* ll_out;       // log-likelihood of the E-step whose statistics these are (nullptr: skip)
+    double* ll_ring;      // ring of log-likelihoods of the E-steps whose statistics these are (nullptr: skip)
+    unsigned long long* ll_counter;   // device-side step counter: the ring slot written is *ll_counter % ring, then it is incremented
+    int ll_ring_len;
 };
 
 __global__ void em_finalize_kernel(const EmFinalizeArgs p)
@@ -518,10 +520,13 @@ __global__ void em_finalize_kernel(const EmFinalizeArgs p)
         else p.theta_out[((j * (NT / 2) + nt / 2) * 32 + lane) * 2 + (nt & 1)] = val;
     }
     if (tid == 0) p.theta_out[p.ne * NT * 32 + kc] = real ? s_const : -INFINITY;
-    if (p.ll_out && p.vsum && kc == 0 && tid == 0) {
+    if (p.ll_ring && p.vsum && kc == 0 && tid == 0) {
         const double ll_sum = tree8(p.vsum + (p.SV - 8), p.SV);
-        // mean over points minus D log(2 pi) / 2 (EM.cpp:197-211)
-        *p.ll_out = ll_sum / static_cast<double>(p.n_total) - 0.5 * d * log(2.0 * 3.14159265358979323846);
+        // mean over points minus D log(2 pi) / 2 (EM.cpp:197-211).  The slot comes from a device-side counter so that
+        // the launch arguments are the same for every step (the step is replayed from a CUDA graph).
+        const unsigned long long idx = *p.ll_counter;
+        p.ll_ring[idx % p.ll_ring_len] = ll_sum / static_cast<double>(p.n_total) - 0.5 * d * log(2.0 * 3.14159265358979323846);
+        *p.ll_counter = idx + 1;
     }
 }
 
@@ -557,6 +562,7 @@ struct EmGpu {
     double* partials = nullptr;
     double* vsum = nullptr;
     double* ll = nullptr;      // ring of log-likelihoods
+    unsigned long long* ll_counter = nullptr;   // device-side count of completed steps (selects the ring slot)
     int2* feat_m = nullptr;
     int2* feat_e = nullptr;
     unsigned* counter = nullptr;
@@ -596,6 +602,11 @@ struct mlb_em {
     size_t smem_split_e = 0, smem_split_m = 0;
     size_t smem_fused = 0;       // dynamic shared memory of the fused kernels (em_small_kernel for D <= 8, em_kernel for D = 16)
     int MW = 4;                  // split M kernel: feature tiles per warp
+    // One EM step as a CUDA graph per theta-slot parity (single-GPU contexts): replayed instead of re-launching the
+    // 6-8 small operations of a step, which is what bounds small problems (BASELINE config 1: N = 10k).
+    cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+    int64_t launches_per_step = 0;
+    int plain_steps = 0;         // steps launched the ordinary way since creation (the first two size the scratch buffers)
 
     double* means(int g) const { return gpus[g].params; }
     double* covs(int g) const { return gpus[g].params + d * k; }
@@ -704,7 +715,7 @@ static int launch_pass(mlb_em* em, int g, const double* theta, bool timed)
     return launch_em(em, em->fn_step, a, g, em->gpus[g].grid);
 }
 
-static EmFinalizeArgs finalize_args(const mlb_em* em, int g, bool from_stats, int theta_slot, double* ll_out)
+static EmFinalizeArgs finalize_args(const mlb_em* em, int g, bool from_stats, int theta_slot, bool want_ll)
 {
     const EmGpu& eg = em->gpus[g];
     EmFinalizeArgs f{};
@@ -717,16 +728,16 @@ static EmFinalizeArgs finalize_args(const mlb_em* em, int g, bool from_stats, in
     f.means = em->means(g); f.covs = em->covs(g); f.weights = em->weights(g);
     f.inv_covs = em->inv_covs(g); f.sqrt_dets = em->sqrt_dets(g);
     f.theta_out = eg.theta[theta_slot];
-    f.ll_out = ll_out;
+    f.ll_ring = want_ll ? eg.ll : nullptr;
+    f.ll_counter = eg.ll_counter;
+    f.ll_ring_len = kLlRing;
     return f;
 }
 
-static int launch_finalize(mlb_em* em, int g, bool from_stats, int theta_slot, double* ll_out)
+static int launch_finalize(mlb_em* em, int g, bool from_stats, int theta_slot, bool want_ll)
 {
-    const EmFinalizeArgs f = finalize_args(em, g, from_stats, theta_slot, ll_out);
+    const EmFinalizeArgs f = finalize_args(em, g, from_stats, theta_slot, want_ll);
     const size_t smem = sizeof(double) * (3 * em->d * em->d + 3 * em->d);
-    if (smem > 48 * 1024)
-        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em_finalize_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     em_finalize_kernel<<<em->KP, 128, smem, em->ctx->gpus[g].stream>>>(f);
     MLB_CUDA(cudaGetLastError());
     ++em->launches;
@@ -734,10 +745,9 @@ static int launch_finalize(mlb_em* em, int g, bool from_stats, int theta_slot, d
 }
 
 // E+M over all local points, statistics reduced and exchanged, parameters refreshed into the other theta slot.
-static int enqueue_step(mlb_em* em)
+static int enqueue_step_plain(mlb_em* em)
 {
     mlb_ctx* ctx = em->ctx;
-    const int ll_slot = static_cast<int>(em->steps_done % kLlRing);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
         return launch_pass(em, g, em->gpus[g].theta[em->cur], true);
     }));
@@ -746,8 +756,45 @@ static int enqueue_step(mlb_em* em)
     MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV));
     em->launches += static_cast<int64_t>(ctx->gpus.size());
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
-        return launch_finalize(em, g, true, em->cur ^ 1, em->gpus[g].ll + ll_slot);
+        return launch_finalize(em, g, true, em->cur ^ 1, true);
     }));
+    return MLB_OK;
+}
+
+static int enqueue_step(mlb_em* em)
+{
+    mlb_ctx* ctx = em->ctx;
+    // Graph replay: one local GPU, no collective in the step, no per-launch event timing, and the scratch buffers
+    // already sized by two ordinary steps (nothing may allocate while a stream is being captured).
+    const bool graphable = ctx->gpus.size() == 1 && ctx->world == 1 && !em->gpus[0].timer.enabled && em->plain_steps >= 2;
+    if (!graphable) {
+        MLB_TRY(enqueue_step_plain(em));
+        ++em->plain_steps;
+        em->cur ^= 1;
+        return MLB_OK;
+    }
+    Gpu& gpu = ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    cudaGraphExec_t& exec = em->step_graph[em->cur];
+    if (!exec) {
+        const int64_t launches_before = em->launches;
+        cudaGraph_t graph = nullptr;
+        MLB_CUDA(cudaStreamBeginCapture(gpu.stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_step_plain(em);
+        const cudaError_t end = cudaStreamEndCapture(gpu.stream, &graph);
+        if (rc != MLB_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        MLB_CUDA(end);
+        em->launches_per_step = em->launches - launches_before;
+        em->launches = launches_before;   // nothing ran yet: the capture only recorded the work
+        const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        MLB_CUDA(inst);
+    }
+    MLB_CUDA(cudaGraphLaunch(exec, gpu.stream));
+    em->launches += em->launches_per_step;
     em->cur ^= 1;
     return MLB_OK;
 }
@@ -865,6 +912,13 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         MLB_CUDA(cudaMallocAsync(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&eg.vsum, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&eg.ll, sizeof(double) * kLlRing, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&eg.ll_counter, sizeof(unsigned long long), gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(eg.ll_counter, 0, sizeof(unsigned long long), gpu.stream));
+        {
+            const size_t fin_smem = sizeof(double) * (3 * em->d * em->d + 3 * em->d);
+            if (fin_smem > 48 * 1024)
+                MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em_finalize_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)));
+        }
         MLB_CUDA(cudaMallocAsync(&eg.feat_m, sizeof(int2) * em->feat_m.size(), gpu.stream));
         MLB_CUDA(cudaMallocAsync(&eg.feat_e, sizeof(int2) * em->feat_e.size(), gpu.stream));
         MLB_CUDA(cudaMallocAsync(&eg.counter, sizeof(unsigned), gpu.stream));
@@ -909,13 +963,15 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
 int mlb_em_destroy(mlb_em* em)
 {
     if (!em) return MLB_OK;
+    for (cudaGraphExec_t& ge : em->step_graph)
+        if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
     for (size_t g = 0; g < em->gpus.size(); ++g) {
         cudaSetDevice(em->ctx->gpus[g].device);
         cudaStreamSynchronize(em->ctx->gpus[g].stream);
         EmGpu& eg = em->gpus[g];
         eg.timer.destroy();
         for (void* ptr : {static_cast<void*>(eg.theta[0]), static_cast<void*>(eg.theta[1]), static_cast<void*>(eg.params),
-                          static_cast<void*>(eg.partials), static_cast<void*>(eg.vsum), static_cast<void*>(eg.ll),
+                          static_cast<void*>(eg.partials), static_cast<void*>(eg.vsum), static_cast<void*>(eg.ll), static_cast<void*>(eg.ll_counter),
                           static_cast<void*>(eg.feat_m), static_cast<void*>(eg.feat_e), static_cast<void*>(eg.counter),
                           static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels), static_cast<void*>(eg.r),
                           static_cast<void*>(eg.feat_e_off)})
@@ -933,7 +989,7 @@ int mlb_em_set_params(mlb_em* em, const double* means, const double* covariances
         MLB_CUDA(cudaMemcpyAsync(em->means(g), means, sizeof(double) * dk, cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(em->covs(g), covariances, sizeof(double) * kdd, cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(em->weights(g), weights, sizeof(double) * em->k, cudaMemcpyHostToDevice, gpu.stream));
-        MLB_TRY(launch_finalize(em, g, false, em->cur, nullptr));
+        MLB_TRY(launch_finalize(em, g, false, em->cur, false));
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));  // the host buffers may go away
         return MLB_OK;
     }));
@@ -1070,7 +1126,7 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
             em->launches += static_cast<int64_t>(ctx->gpus.size());
         }
         if (rc == MLB_OK)
-            rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, true, em->cur, nullptr); });
+            rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, true, em->cur, false); });
         if (rc == MLB_OK) rc = mlb_ctx_synchronize(ctx);
     }
     for (size_t g = 0; g < dev.size(); ++g)
