@@ -14,6 +14,9 @@
 #pragma once
 
 constexpr int kSmallSub = 16;   // points per warp sub-tile
+#ifndef MLB_EM_SMALL_MINB
+#define MLB_EM_SMALL_MINB 4
+#endif
 
 // Slot of the constant-1 feature (weighted count): the first dead E-step slot if the packing has one (DQ odd), else a
 // new slot after the last E-step slot.
@@ -22,14 +25,15 @@ __host__ __device__ constexpr int em_small_nm(int DP) { return (((DP / 4) % 2 ==
 
 constexpr size_t em_small_smem_bytes(int DP, int KP)
 {
-    return sizeof(double) * (em_theta_len(DP, KP) + 4 * kSmallSub * (DP + 4) + 4 * kSmallSub * (em_small_nm(DP) * 8 + 4) + 4 * kSmallSub * (KP + 4) + 8 + DP + kExpTableSize);
+    return sizeof(double) * (em_theta_len(DP, KP) + 4 * kSmallSub * (em_small_nm(DP) * 8 + 4) + 4 * kSmallSub * (KP + 4) + 8 + DP + kExpTableSize);
 }
 
 template <int DP, int KP, int MODE>
-__global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) * (KP / 8) <= 12) ? 4 : 3)) em_small_kernel(const EmArgs p)
+__global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) * (KP / 8) <= 12) ? MLB_EM_SMALL_MINB : 3)) em_small_kernel(const EmArgs p)
 {
     constexpr int NT = KP / 8, DQ = DP / 4, NE = em_ne(DP), NM = em_small_nm(DP);
-    constexpr int ZS = DP + 4, RS = KP + 4, PS = NM * 8 + 4;
+    constexpr int RS = KP + 4, PS = NM * 8 + 4;
+    constexpr int LIN = (NE - DQ) * 4;   // the linear slots of a feature row hold z itself: the point tile lives there
     constexpr int SV = em_sv(DP, KP);
     constexpr int XR = (kSmallSub * DP + 31) / 32;
     constexpr int CS = em_small_count_slot(DP);
@@ -38,8 +42,7 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
     extern __shared__ __align__(16) double sm[];
     double* thE = sm;
     double* cE = thE + NE * NT * 32;
-    double* Zw = cE + KP;                         // [4][16][ZS]
-    double* Phi = Zw + 4 * kSmallSub * ZS;        // [4][16][PS]; reused as the chunk-end reduction buffer
+    double* Phi = cE + KP;                        // [4][16][PS] feature rows (products | z | count); reused as the chunk-end reduction buffer
     double* Rw = Phi + 4 * kSmallSub * PS;        // [4][16][RS]
     double* wl = Rw + 4 * kSmallSub * RS;
     double* sh = wl + 8;
@@ -51,13 +54,11 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
 
     if (MODE != 1)
         for (int i = tid; i < em_theta_len(DP, KP); i += kEmThreads) sm[i] = p.theta[i];
-    for (int i = tid; i < 4 * kSmallSub * ZS; i += kEmThreads) Zw[i] = 0.0;
     for (int i = tid; i < 4 * kSmallSub * PS; i += kEmThreads) Phi[i] = 0.0;
     for (int i = tid; i < 4 * kSmallSub * RS; i += kEmThreads) Rw[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
     load_exp_table(etab);
 
-    double* Z = Zw + warp * kSmallSub * ZS;
     double* F = Phi + warp * kSmallSub * PS;
     double* R = Rw + warp * kSmallSub * RS;
 
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
             if (e < kSmallSub * d) {
                 const int pt = (d == DP) ? e / DP : FastDiv(d).div(e);
                 const int dm = e - pt * d;
-                Z[pt * ZS + dm] = e < nel ? xr[r] - sh[dm] : 0.0;
+                F[pt * PS + LIN + dm] = e < nel ? xr[r] - sh[dm] : 0.0;
             }
         }
         if (lane < kSmallSub) F[lane * PS + CS] = lane < nvalid ? 1.0 : 0.0;   // the count feature
@@ -118,8 +119,8 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
             if (t + 4 < nsubs) load_sub(tile0 + 4 * kSmallSub, static_cast<int>(min64(kSmallSub, p_end - tile0 - 4 * kSmallSub)));
             __syncwarp();
 
-            const double* z0 = Z + g * ZS;
-            const double* z1 = z0 + 8 * ZS;
+            const double* z0 = F + g * PS + LIN;
+            const double* z1 = z0 + 8 * PS;
             double* f0 = F + g * PS + c;
             double* f1 = f0 + 8 * PS;
             double zc0[DQ], zc1[DQ];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
                 estep(J0 + 2 * DQ + h, u0, u1, live);
             }
 #pragma unroll
-            for (int m = 0; m < DQ; ++m) estep(NE - DQ + m, zc0[m], zc1[m], true);
+            for (int m = 0; m < DQ; ++m) estep(NE - DQ + m, zc0[m], zc1[m], false);   // already in the row
 
             if (MODE == 1) {
                 // responsibilities given by the caller (maximise_first, EM.cpp:120-125)
