@@ -341,9 +341,13 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
     __shared__ int s_next;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int own_lo = warp * (KP / 8), own_hi = own_lo + KP / 8;
+    const bool reg_counts = KP / 8 <= 32;   // each lane keeps the count of one owned cluster in a register
 
     for (int i = tid; i < KP * SD; i += kStThreads) sums[i] = 0.0;
     if (tid < d) sh[tid] = p.shift[tid];
+    __syncthreads();
+    const double sh0 = lane < d ? sh[lane] : 0.0, sh1 = lane + 32 < d ? sh[lane + 32] : 0.0;
+    double cnt = 0.0;
 
     for (;;) {
         __syncthreads();
@@ -382,41 +386,23 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
             for (int base = 0; base < kStTile; base += 32) {
                 const int lab = labs[base + lane];
                 unsigned mask = __ballot_sync(0xffffffffu, lab >= own_lo && lab < own_hi);
-                // Four owned points at a time: when their clusters are all different the four read-add-write chains are
-                // independent and run concurrently; otherwise (two points of one cluster) they run one after the other, so
-                // every cluster still receives its points in index order.
                 while (mask) {
-                    int b[4], kk[4];
-                    int nb = 0;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        b[u] = mask ? __ffs(mask) - 1 : 0;
-                        kk[u] = __shfl_sync(0xffffffffu, lab, b[u]);
-                        if (mask) { ++nb; mask &= mask - 1; }
-                    }
-                    const bool distinct = nb == 4 && kk[0] != kk[1] && kk[0] != kk[2] && kk[0] != kk[3] && kk[1] != kk[2] && kk[1] != kk[3] && kk[2] != kk[3];
-                    if (distinct) {
-                        for (int l = lane; l <= d; l += 32) {
-                            double v[4], cur[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                v[u] = l < d ? X[static_cast<size_t>(base + b[u]) * d + l] - sh[l] : 1.0;   // slot d is the count
-                                cur[u] = sums[static_cast<size_t>(kk[u]) * SD + l];
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) sums[static_cast<size_t>(kk[u]) * SD + l] = cur[u] + v[u];
-                        }
-                    } else {
-                        for (int u = 0; u < nb; ++u) {
-                            const double* xr = X + static_cast<size_t>(base + b[u]) * d;
-                            double* sk = sums + static_cast<size_t>(kk[u]) * SD;
-                            for (int l = lane; l <= d; l += 32) sk[l] += l < d ? xr[l] - sh[l] : 1.0;
-                        }
-                    }
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int kk = __shfl_sync(0xffffffffu, lab, b);
+                    const double* xr = X + static_cast<size_t>(base + b) * d;
+                    double* sk = sums + static_cast<size_t>(kk) * SD;
+                    if (lane < d) sk[lane] += xr[lane] - sh0;
+                    if (DP > 32 && lane + 32 < d) sk[lane + 32] += xr[lane + 32] - sh1;
+                    if (reg_counts) cnt += (kk - own_lo == lane) ? 1.0 : 0.0;   // lane j counts cluster own_lo + j
+                    else if (lane == 0) sk[d] += 1.0;
                 }
             }
             __syncthreads();
         }
+        if (reg_counts && lane < KP / 8) sums[static_cast<size_t>(own_lo + lane) * SD + d] = cnt;
+        cnt = 0.0;
+        __syncthreads();
         double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
         for (int i = tid; i < KP * SD; i += kStThreads) {
             out[i] = sums[i];
