@@ -98,6 +98,10 @@ __device__ __forceinline__ void km_cp_async_wait() { asm volatile("cp.async.wait
 
 // ---------------------------------------------------------------- assignment (KMeans.cpp:153-178)
 // Writes the labels and, per chunk, the inertia and the number of changed labels (slots KP*(d+1) and +1 of the partial).
+// Every warp works on its own 16-point sub-tiles (its own cp.async double buffer, only __syncwarp inside a chunk), so the
+// exact refinement of one warp (global loads of centroid rows) overlaps the tensor-pipe filter of the others.
+constexpr int kKmSub = 16;   // points per warp sub-tile
+
 template <int DP>
 __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
 {
@@ -106,11 +110,11 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
     const int KP = p.KP, d = p.d, SD = d + 1;
     double* Bf = sm;                                  // DP * KP
     double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
-    double* Xb = nrm + KP;                            // 2 x kKmTile * XS, raw coordinates (padding columns zero), double-buffered
+    double* Xb = nrm + KP;                            // [4 warps][2 buffers][16][XS], raw coordinates (padding columns zero)
     double* sh = Xb + 2 * kKmTile * XS;               // DP
     double* red = sh + DP;                            // 16
-    int* labs = reinterpret_cast<int*>(red + 16);     // kKmTile: the filter's verdict (~label: ambiguous under its rounding bound)
-    unsigned* oldl = reinterpret_cast<unsigned*>(labs + kKmTile);  // 2 x kKmTile: previous labels, double-buffered
+    int* labs_all = reinterpret_cast<int*>(red + 16); // [4][16]: the filter's verdict (~label: ambiguous under its rounding bound)
+    unsigned* oldl_all = reinterpret_cast<unsigned*>(labs_all + kKmTile);  // [4][2][16]: previous labels
     __shared__ int s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
@@ -124,28 +128,32 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
     for (int j = 0; j < DQ; ++j) shc[j] = sh[4 * j + c];
     const double u_bound = 8.0 * (d + 4) * 1.1102230246251565e-16;
     const double cmax = *p.cmax;
+    double* Xw = Xb + warp * (2 * kKmSub * XS);
+    int* labs = labs_all + warp * kKmSub;
+    unsigned* oldw = oldl_all + warp * (2 * kKmSub);
 
-    // Asynchronous copy of one tile of points (and their previous labels) into buffer `buf`; rows past the end are zeroed.
+    // Asynchronous copy of one sub-tile of points (and their previous labels) into the warp's buffer `buf`; rows past the
+    // end are zeroed.
     const FastDiv by_d(d);
     auto stage = [&](long long tile0, int nvalid, int buf) {
-        double* X = Xb + buf * (kKmTile * XS);
+        double* X = Xw + buf * (kKmSub * XS);
         const double* xg = p.x + tile0 * d;
         const int nel = nvalid * d;
         if (d == DP) {
             // rows are 16-byte aligned on both sides: two coordinates per copy, row index by a shift
-            for (int e2 = tid; e2 < kKmTile * (DP / 2); e2 += kKmThreads) {
+            for (int e2 = lane; e2 < kKmSub * (DP / 2); e2 += 32) {
                 const int pt = e2 / (DP / 2), q = e2 - pt * (DP / 2);
                 if (2 * e2 < nel) km_cp_async16(X + pt * XS + 2 * q, xg + 2 * e2);
                 else *reinterpret_cast<double2*>(X + pt * XS + 2 * q) = make_double2(0.0, 0.0);
             }
         } else {
-            for (int e = tid; e < kKmTile * d; e += kKmThreads) {
+            for (int e = lane; e < kKmSub * d; e += 32) {
                 const int pt = by_d.div(e), dm = e - pt * d;
                 if (e < nel) km_cp_async8(X + pt * XS + dm, xg + e);
                 else X[pt * XS + dm] = 0.0;
             }
         }
-        if (tid < nvalid) km_cp_async4(oldl + buf * kKmTile + tid, p.labels + tile0 + tid);
+        if (lane < nvalid) km_cp_async4(oldw + buf * kKmSub + lane, p.labels + tile0 + lane);
         km_cp_async_commit();
     };
 
@@ -157,27 +165,30 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
         if (chunk >= p.n_chunks) break;
         const long long p_begin = static_cast<long long>(chunk) * p.chunk;
         const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
-        const int ntiles = static_cast<int>((p_end - p_begin + kKmTile - 1) / kKmTile);
+        const int nsubs = static_cast<int>((p_end - p_begin + kKmSub - 1) / kKmSub);
         double inertia_acc = 0.0;
         int changed_acc = 0;
 
-        stage(p_begin, static_cast<int>(p_end - p_begin < kKmTile ? p_end - p_begin : kKmTile), 0);
-        for (int t = 0; t < ntiles; ++t) {
-            const long long tile0 = p_begin + static_cast<long long>(t) * kKmTile;
-            const int nvalid = static_cast<int>(p_end - tile0 < kKmTile ? p_end - tile0 : kKmTile);
-            if (t + 1 < ntiles) {
-                const long long next0 = tile0 + kKmTile;
-                stage(next0, static_cast<int>(p_end - next0 < kKmTile ? p_end - next0 : kKmTile), (t + 1) & 1);
+        // warp w takes the sub-tiles w, w + 4, w + 8, ... of the chunk
+        auto sub_begin = [&](int t) { return p_begin + static_cast<long long>(t) * kKmSub; };
+        auto sub_valid = [&](int t) { const long long left = p_end - sub_begin(t); return static_cast<int>(left < kKmSub ? left : kKmSub); };
+        if (warp < nsubs) stage(sub_begin(warp), sub_valid(warp), 0);
+        int it = 0;
+        for (int t = warp; t < nsubs; t += 4, ++it) {
+            const long long tile0 = sub_begin(t);
+            const int nvalid = sub_valid(t);
+            if (t + 4 < nsubs) {
+                stage(sub_begin(t + 4), sub_valid(t + 4), (it + 1) & 1);
                 km_cp_async_wait<1>();
             } else {
                 km_cp_async_wait<0>();
             }
-            __syncthreads();
-            const double* X = Xb + (t & 1) * (kKmTile * XS);
-            const unsigned* old_labels = oldl + (t & 1) * kKmTile;
+            __syncwarp();
+            const double* X = Xw + (it & 1) * (kKmSub * XS);
+            const unsigned* old_labels = oldw + (it & 1) * kKmSub;
 
             // ---------------- filter: scores of this warp's 16 points against all centroids
-            const double* x0 = X + (warp * 16 + g) * XS;
+            const double* x0 = X + g * XS;
             const double* x1 = x0 + 8 * XS;
             double z0[DQ], z1[DQ];
             double zz0 = 0.0, zz1 = 0.0;
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
                     secondk[mt] = min(min(secondk[mt], os), max(bestk[mt], ob));
                     if (ob < bestk[mt] || (ob == bestk[mt] && ok < bk[mt])) { bestk[mt] = ob; bk[mt] = ok; }
                 }
-                const int pl = warp * 16 + mt * 8 + g;
+                const int pl = mt * 8 + g;
                 if (c == 0) {
                     // best score <= best_hi, second score >= second_lo; tau bounds the FP64 rounding of a score
                     const double best_hi = __hiloint2double(bestk[mt] + 1, 0);
@@ -258,7 +269,7 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
             // continues the same fused-multiply-add chain over the second half: the same value, with the centroid row's
             // global loads of both halves in flight together.
             {
-                const int pl = warp * 16 + (lane >> 1), half = lane & 1;
+                const int pl = lane >> 1, half = lane & 1;
                 const bool valid = pl < nvalid;
                 const double* xr = X + pl * XS;
                 const int hd = (d + 1) / 2;
@@ -302,10 +313,10 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
                     p.labels[tile0 + pl] = static_cast<unsigned>(label);
                 }
             }
-            __syncthreads();   // the buffers are refilled by the stage() of the next iteration
+            __syncwarp();   // the buffer and the verdicts are rewritten two sub-tiles later / by the next sub-tile
         }
 
-        // ---------------- the chunk's inertia and changed-label count
+        // ---------------- the chunk's inertia and changed-label count: fixed order inside the warp and across the warps
         double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
