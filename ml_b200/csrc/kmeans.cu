@@ -1,17 +1,19 @@
 // K-means (Lloyd) on B200 (sm_100a), FP64.  Replaces the loops of ML/KMeans.cpp:
-//     assignment_step + assign_label   KMeans.cpp:153-178
-//     update_step                      KMeans.cpp:180-192
+//     assignment_step + assign_label   KMeans.cpp:153-178     km_assign_kernel
+//     update_step                      KMeans.cpp:180-192     km_stats_kernel / km_stats_small_kernel + km_update_kernel
 //
-// Assignment = filter + exact refinement (DESIGN.md "K-means kernels").
-//   filter:  score_ik = |c'_k|^2 - 2 z_i . c'_k  (z = x - shift, c' = c - shift) for all K centroids as
-//            a [points x D] x [D x K] product on the FP64 tensor pipe (mma.sync.m8n8k4.f64), tracking
-//            the best and second-best score per point;
-//   refine:  the winner's squared distance is recomputed exactly as the reference does
-//            ((x - c).squaredNorm(), sequential over the dimensions) so labels, distances and inertia are
-//            the reference's; a point whose two best scores are closer than the rounding bound of the
-//            filter is re-assigned by the exact scan over all K (strict <, lowest k wins).
-// Update statistics (per-cluster count and sum of z) are accumulated in shared memory by the warp
-// that owns the cluster, in point order: no floating-point atomics, bitwise reproducible.
+// Assignment = filter + exact refinement (DESIGN.md "K-means").
+//   filter:  d2_ik = |z_i|^2 + |c'_k|^2 - 2 z_i . c'_k  (z = x - shift, c' = c - shift) for all K centroids as a
+//            [points x D] x [D x K] product on the FP64 tensor pipe (mma.sync.m8n8k4.f64), tracking the best and
+//            second-best score per point on 32-bit integer keys (the high word of the non-negative double);
+//   refine:  the winner's squared distance is recomputed exactly as the reference does ((x - c).squaredNorm(),
+//            sequential over the dimensions) so labels, distances and inertia are the reference's; a point whose two
+//            best keys cannot be separated (key truncation + FP64 rounding bound) is re-assigned by the exact scan
+//            over all K (strict <, lowest k wins).
+// Every warp works on its own 16-point sub-tiles (own cp.async double buffer), so one warp's refinement overlaps the
+// other warps' filter.  Update statistics (per-cluster count and sum of z) are a separate kernel: for K > 32 the warp
+// that owns a cluster adds its points in index order into shared memory; for K <= 32 a one-hot tensor-pipe product.
+// No floating-point atomics anywhere: bitwise reproducible, and identical for every GPU count.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -422,6 +424,118 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
     }
 }
 
+// ---------------------------------------------------------------- update statistics, K <= 32
+// With few clusters the owner-warp scheme above leaves most warps idle (K = 3: one warp does everything).  Here the
+// statistics are a tensor-pipe product instead: S[k][col] = sum_i onehot(label_i == k) * [z_i, 1][col], a
+// [32 x points] x [points x (D+1)] DMMA with the one-hot operand made from the labels in registers.  Every warp runs
+// its own 16-point sub-tiles; the order of the additions is the hardware's fixed one, so the result is reproducible;
+// the four warps' accumulators are combined in a fixed order at the end of a chunk.  2 * 32 * (D + 1) flops per point.
+template <int DP>
+__global__ void __launch_bounds__(kKmThreads) km_stats_small_kernel(const KmArgs p)
+{
+    constexpr int NTD = (DP + 1 + 7) / 8, ZS = 8 * NTD + 4, XR = (kKmSub * DP + 31) / 32;
+    extern __shared__ __align__(16) double sm[];
+    const int d = p.d, SD = d + 1;
+    double* Zw = sm;                                  // [4][16][ZS]: z, then the constant 1 (0 past the end), zero padding
+    double* redbuf = Zw + 4 * kKmSub * ZS;            // [32][8 * NTD] chunk-end combination
+    double* sh = redbuf + 32 * 8 * NTD;               // DP
+    __shared__ int s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+
+    for (int i = tid; i < 4 * kKmSub * ZS; i += kKmThreads) Zw[i] = 0.0;
+    if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
+    __syncthreads();
+    double* Z = Zw + warp * kKmSub * ZS;
+    const FastDiv by_d(d);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = static_cast<int>(atomicAdd(p.counter, 1u));
+        __syncthreads();
+        const int chunk = s_next;
+        if (chunk >= p.n_chunks) break;
+        const long long p_begin = static_cast<long long>(chunk) * p.chunk;
+        const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
+        const int nsubs = static_cast<int>((p_end - p_begin + kKmSub - 1) / kKmSub);
+        double acc[4][NTD][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NTD; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int t = warp; t < nsubs; t += 4) {
+            const long long tile0 = p_begin + static_cast<long long>(t) * kKmSub;
+            const int nvalid = static_cast<int>(p_end - tile0 < kKmSub ? p_end - tile0 : kKmSub);
+            const double* xg = p.x + tile0 * d;
+            const int nel = nvalid * d;
+            double xr[XR];
+#pragma unroll
+            for (int r = 0; r < XR; ++r) {
+                const int e = lane + 32 * r;
+                xr[r] = e < nel ? __ldg(xg + e) : 0.0;
+            }
+            const int label = lane < nvalid ? static_cast<int>(p.labels[tile0 + lane]) : -1;
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < XR; ++r) {
+                const int e = lane + 32 * r;
+                if (e < kKmSub * d) {
+                    const int pt = (d == DP) ? e / DP : by_d.div(e);
+                    const int dm = e - pt * d;
+                    Z[pt * ZS + dm] = e < nel ? xr[r] - sh[dm] : 0.0;
+                }
+            }
+            if (lane < kKmSub) Z[lane * ZS + d] = lane < nvalid ? 1.0 : 0.0;   // the count column sits right after the coordinates
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < kKmSub / 4; ++s) {
+                const int lab = __shfl_sync(0xffffffffu, label, 4 * s + c);
+                const double* zp = Z + (4 * s + c) * ZS + g;
+                double bf[NTD];
+#pragma unroll
+                for (int j = 0; j < NTD; ++j) bf[j] = zp[8 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double onehot = lab == 8 * i + g ? 1.0 : 0.0;
+#pragma unroll
+                    for (int j = 0; j < NTD; ++j) km_dmma(acc[i][j], onehot, bf[j]);
+                }
+            }
+        }
+        // ---------------- the four warps' statistics in the fixed order ((w0 + w1) + w2) + w3, then out[k][0..d] = sums, count
+        for (int w = 0; w < 4; ++w) {
+            __syncthreads();
+            if (warp == w) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NTD; ++j) {
+                        double2* cell = reinterpret_cast<double2*>(redbuf + (8 * i + g) * (8 * NTD) + 8 * j + 2 * c);
+                        double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+                        if (w > 0) {
+                            const double2 o = *cell;
+                            v.x = o.x + v.x;
+                            v.y = o.y + v.y;
+                        }
+                        *cell = v;
+                    }
+            }
+        }
+        __syncthreads();
+        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, p.KP);
+        for (int i = tid; i < p.KP * SD; i += kKmThreads) {
+            const int kk = i / SD, col = i - kk * SD;
+            out[i] = redbuf[kk * (8 * NTD) + col];
+        }
+    }
+}
+
+inline size_t km_stats_small_smem_bytes(int DP)
+{
+    const int NTD = (DP + 1 + 7) / 8;
+    return sizeof(double) * (4 * kKmSub * (8 * NTD + 4) + 32 * 8 * NTD + DP);
+}
+
 // Builds the filter's image of the centroids: -2 c' in mma B-fragment order and |c'|^2; one thread per (dimension, centroid).
 struct KmPrepArgs {
     const double* craw;   // D x K
@@ -510,6 +624,17 @@ static KmKernelFn km_kernel_for(int DP)
     }
 }
 
+static KmKernelFn km_stats_small_kernel_for(int DP)
+{
+    switch (DP) {
+    case 4: return km_stats_small_kernel<4>;
+    case 8: return km_stats_small_kernel<8>;
+    case 16: return km_stats_small_kernel<16>;
+    case 32: return km_stats_small_kernel<32>;
+    default: return nullptr;
+    }
+}
+
 static KmKernelFn km_stats_kernel_for(int DP)
 {
     switch (DP) {
@@ -547,6 +672,7 @@ struct mlb_km {
     int d = 0, k = 0, DP = 0, KP = 0, SV = 0;
     std::vector<KmGpu> gpus;
     KmKernelFn fn = nullptr, fn_stats = nullptr;
+    bool stats_small = false;
     size_t smem = 0, smem_stats = 0;
     bool have_centroids = false, have_stats = false;
     int64_t launches = 0;
@@ -583,12 +709,13 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         if (d <= cand) { DP = cand; break; }
     MLB_REQUIRE(DP, "mlb_km_create: D=%d not supported by this build (D <= 64)", d);
     const int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup;
-    const size_t smem = km_smem_bytes(DP, KP), smem_stats = km_stats_smem_bytes(d, KP);
+    const size_t smem = km_smem_bytes(DP, KP), smem_stats = (KP == kKmGroup && DP <= 32) ? km_stats_small_smem_bytes(DP) : km_stats_smem_bytes(d, KP);
     MLB_REQUIRE(std::max(smem, smem_stats) <= 227 * 1024, "mlb_km_create: D=%d, K=%d needs %zu bytes of shared memory (limit 232448)", d, k, std::max(smem, smem_stats));
     auto* km = new mlb_km;
     km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->SV = km_sv(d, KP);
     km->fn = km_kernel_for(DP);
-    km->fn_stats = km_stats_kernel_for(DP);
+    km->stats_small = KP == kKmGroup && DP <= 32;   // K <= 32: one-hot tensor-pipe statistics (its accumulators fit the registers up to D = 32)
+    km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : km_stats_kernel_for(DP);
     km->smem = smem;
     km->smem_stats = smem_stats;
     km->gpus.resize(ctx->gpus.size());
@@ -615,7 +742,7 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means kernel does not fit on an SM");
         kg.grid = per_sm * sms;
         MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn_stats), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stats)));
-        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn_stats), kStThreads, smem_stats));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn_stats), km->stats_small ? kKmThreads : kStThreads, smem_stats));
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means statistics kernel does not fit on an SM");
         kg.grid_stats = per_sm * sms;
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
@@ -688,7 +815,7 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
             km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
             MLB_CUDA(cudaGetLastError());
             MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-            km->fn_stats<<<std::min(kg.grid_stats, a.n_chunks), kStThreads, km->smem_stats, gpu.stream>>>(a);
+            km->fn_stats<<<std::min(kg.grid_stats, a.n_chunks), km->stats_small ? kKmThreads : kStThreads, km->smem_stats, gpu.stream>>>(a);
             MLB_CUDA(cudaGetLastError());
             MLB_TRY(kg.timer.end(gpu.stream));
             km->launches += 2;
