@@ -833,10 +833,10 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         KP = pad_to(k, kps, 3);
         NT = KP / 8;
     } else {
-        // split path: D padded to a multiple of 4, components in groups of 32 (K <= 32) or 64
+        // split path: D padded to a multiple of 4, components in groups of 16 (K <= 16), 32 (K <= 32) or 64
         MLB_REQUIRE(data->d <= 64 && k <= 256, "mlb_em_create: D=%d, K=%d not supported by this build (D <= 64, K <= 256)", data->d, k);
         DP = (data->d + 3) / 4 * 4;
-        const int KG = k > 32 ? 64 : 32;
+        const int KG = k > 32 ? 64 : (k > 16 ? 32 : 16);
         KP = (k + KG - 1) / KG * KG;
         NT = KG / 8;
     }
@@ -850,7 +850,7 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         em->fn_emit = em_kernel_for<2>(DP, KP);
         em->smem_fused = DP <= 8 ? em_small_smem_bytes(DP, KP) : em_smem_bytes(DP, KP);
     } else {
-        em->fn_split_e = NT == 8 ? em_split_e_kernel<8> : em_split_e_kernel<4>;
+        em->fn_split_e = NT == 8 ? em_split_e_kernel<8> : NT == 4 ? em_split_e_kernel<4> : em_split_e_kernel<2>;
         // feature tiles per warp of the M kernel: the choice that wastes the fewest tile slots (ties: the larger)
         int best_waste = 1 << 30;
         for (int mw = 3; mw <= 5; ++mw) {
@@ -858,7 +858,8 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
             if (waste <= best_waste) { best_waste = waste; em->MW = mw; }
         }
         if (NT == 8) em->fn_split_m = em->MW == 3 ? em_split_m_kernel<8, 3> : em->MW == 4 ? em_split_m_kernel<8, 4> : em_split_m_kernel<8, 5>;
-        else em->fn_split_m = em->MW == 3 ? em_split_m_kernel<4, 3> : em->MW == 4 ? em_split_m_kernel<4, 4> : em_split_m_kernel<4, 5>;
+        else if (NT == 4) em->fn_split_m = em->MW == 3 ? em_split_m_kernel<4, 3> : em->MW == 4 ? em_split_m_kernel<4, 4> : em_split_m_kernel<4, 5>;
+        else em->fn_split_m = em->MW == 3 ? em_split_m_kernel<2, 3> : em->MW == 4 ? em_split_m_kernel<2, 4> : em_split_m_kernel<2, 5>;
         em->smem_split_e = em_split_e_smem(NT, DP, KP);
         em->smem_split_m = em_split_m_smem(NT, DP);
     }

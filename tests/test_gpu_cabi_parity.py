@@ -75,6 +75,7 @@ EM_SPLIT_SHAPES = [
     (5003, 20, 33, 34),
     (10000, 64, 34, 35),
     (2500, 33, 3, 36),
+    (7000, 20, 24, 37),
 ]
 
 
