@@ -10,8 +10,12 @@
 // where theta_k packs -1/2 Sigma_k^-1, Sigma_k^-1 (mu_k - c) and the constant, and S packs the
 // weighted count, first and second moments about c.  Both products run on the FP64 tensor pipe
 // (mma.sync.m8n8k4.f64 -> DMMA.8x8x4), the features are generated in registers from the point
-// tile in shared memory, and the responsibilities never leave the SM.  One fused kernel per
-// iteration reads X exactly once.
+// tile in shared memory.  Three kernel families share this formulation, the partial-statistics
+// layout, the reduction and the parameter refresh below:
+//     em_small_kernel (em_small.cuh)  D <= 8,  K <= 32   fused E+M, every warp on its own 16-point sub-tiles
+//     em_kernel       (this file)     D <= 16, K <= 32   fused E+M, 64-point tiles, M-step split over the warps
+//     em_split_*      (em_split.cuh)  D <= 64, K <= 256  E kernel + M kernel, Theta streamed, R resident in HBM
+// The fused kernels read X exactly once per iteration and the responsibilities never leave the SM.
 //
 // Determinism: per-chunk partial statistics in a fixed layout, chunks are a function of N only,
 // fixed-order reduction (context.cu), no floating-point atomics anywhere.

@@ -1,6 +1,6 @@
 """BASELINE config 1 (Benchmarks/bm_EM.cpp, bm_KMeans.cpp): mouse data, KPP, tolerance 1e-14, through the public cppyml API."""
 import sys, time, json, numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repository root
 import oracle
 from ml_b200 import import_cppyml
 cppyml = import_cppyml()
