@@ -575,6 +575,7 @@ struct EmGpu {
     int grid = 0;
     // split path (general shapes)
     double* r = nullptr;         // [n_local][KP] responsibilities of the last E-step
+    double* ll_tile = nullptr;   // [n_chunks][chunk / 64] per-tile log-likelihood sums (E kernel -> M kernel)
     int2* feat_e_off = nullptr;  // E-step slots as Z-row offsets
     int grid_e = 0, grid_m = 0;
     KernelTimer timer;
@@ -678,6 +679,7 @@ static EmSplitArgs split_args(const mlb_em* em, int g, const double* theta)
     a.ne = em->NE; a.nm = em->NM;
     a.r = eg.r;
     a.partials = eg.partials;
+    a.ll_tile = eg.ll_tile;
     a.sv = em->SV;
     a.chunk = em->data->lay.chunk;
     a.n_chunks = static_cast<int>(sh.n_chunks());
@@ -695,7 +697,8 @@ static int launch_split(mlb_em* em, int g, const double* theta, bool run_e, bool
     if (timed) MLB_TRY(eg.timer.begin(gpu.stream));
     if (run_e) {
         MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
-        em->fn_split_e<<<std::min(eg.grid_e, a.n_chunks), kSpThreads, em->smem_split_e, gpu.stream>>>(a);
+        const long long e_items = static_cast<long long>(a.n_chunks) * (a.chunk / kSpTile);
+        em->fn_split_e<<<static_cast<unsigned>(std::min<long long>(eg.grid_e, e_items)), kSpThreads, em->smem_split_e, gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
         ++em->launches;
     }
@@ -947,6 +950,11 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
             MLB_CUDA(cudaMemcpyAsync(eg.feat_e_off, off.data(), sizeof(int2) * off.size(), cudaMemcpyHostToDevice, gpu.stream));
             MLB_CUDA(cudaStreamSynchronize(gpu.stream));   // `off` is a local
             MLB_CUDA(cudaMallocAsync(&eg.r, sizeof(double) * std::max<int64_t>(1, sh.n()) * KP, gpu.stream));
+            {
+                const size_t n_tiles = static_cast<size_t>(std::max<int64_t>(1, sh.n_chunks())) * (data->lay.chunk / kSpTile);
+                MLB_CUDA(cudaMallocAsync(&eg.ll_tile, sizeof(double) * n_tiles, gpu.stream));
+                MLB_CUDA(cudaMemsetAsync(eg.ll_tile, 0, sizeof(double) * n_tiles, gpu.stream));
+            }
             MLB_CUDA(cudaMemsetAsync(eg.partials, 0, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.stream));
             MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em->fn_split_e), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(em->smem_split_e)));
             MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em->fn_split_m), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(em->smem_split_m)));
@@ -978,7 +986,7 @@ int mlb_em_destroy(mlb_em* em)
         for (void* ptr : {static_cast<void*>(eg.theta[0]), static_cast<void*>(eg.theta[1]), static_cast<void*>(eg.params),
                           static_cast<void*>(eg.partials), static_cast<void*>(eg.vsum), static_cast<void*>(eg.ll), static_cast<void*>(eg.ll_counter),
                           static_cast<void*>(eg.feat_m), static_cast<void*>(eg.feat_e), static_cast<void*>(eg.counter),
-                          static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels), static_cast<void*>(eg.r),
+                          static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels), static_cast<void*>(eg.r), static_cast<void*>(eg.ll_tile),
                           static_cast<void*>(eg.feat_e_off)})
             if (ptr) cudaFreeAsync(ptr, em->ctx->gpus[g].stream);
     }

@@ -24,7 +24,6 @@ namespace mlb {
 constexpr int kSpTile = 64;      // points per tile
 constexpr int kSpThreads = 128;  // 4 warps
 constexpr int kSpJB = 8;         // E-step feature steps per staged Theta block
-constexpr int kSpLogBatch = 8;   // tiles between two log() calls of the log-likelihood partial
 
 struct EmSplitArgs {
     const double* x;        // local points, d doubles each
@@ -37,6 +36,7 @@ struct EmSplitArgs {
     int ne, nm;
     double* r;              // [n_local][KP] responsibilities, a row per point
     double* partials;       // [n_chunks][sv]
+    double* ll_tile;        // [n_chunks][chunk / 64]: log-likelihood sum of every 64-point tile (E kernel -> M kernel)
     int sv;
     int chunk, n_chunks;
     unsigned* counter;
@@ -135,23 +135,29 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_e_kernel(const EmSplit
         sp_cp_async_commit();
     };
 
+    // Work item = one 64-point tile (chunks are multiples of 128 points, so tiles never straddle a chunk): fine enough
+    // to balance 148 SMs whatever the chunk size.  The tile's log-likelihood sum goes to ll_tile; the M kernel adds the
+    // tiles of a chunk in order into the chunk's partial.
+    const int tpc = p.chunk / kSpTile;
+    const int nitems = p.n_chunks * tpc;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_next = static_cast<int>(atomicAdd(p.counter, 1u));
         __syncthreads();
-        const int chunk = s_next;
-        if (chunk >= p.n_chunks) break;
+        const int item = s_next;
+        if (item >= nitems) break;
+        const int chunk = item / tpc, t = item - chunk * tpc;
         const long long p_begin = static_cast<long long>(chunk) * p.chunk;
         const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
-        const int ntiles = static_cast<int>((p_end - p_begin + kSpTile - 1) / kSpTile);
         double ll_acc = 0.0, ll_prod = 1.0;
-
-        for (int t = 0; t < ntiles; ++t) {
+        {
             const long long tile0 = p_begin + static_cast<long long>(t) * kSpTile;
+            if (tile0 >= p_end) {
+                if (tid == 0) p.ll_tile[item] = 0.0;
+                continue;
+            }
             const int nvalid = static_cast<int>(p_end - tile0 < kSpTile ? p_end - tile0 : kSpTile);
             sp_load_z_tile(Z, ZS, p.x, sh, tile0, nvalid, d, DP);
-            // (visibility of Z is covered by the first __syncthreads() of the block loop below)
-
             const double* z0 = Z + (warp * 16 + g) * ZS;
             const double* z1 = z0 + 8 * ZS;
             for (int cg = 0; cg < ngroups; ++cg) {
@@ -225,21 +231,15 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_e_kernel(const EmSplit
                     }
                 }
             }
-            if ((t & (kSpLogBatch - 1)) == kSpLogBatch - 1 || t + 1 == ntiles) {
-                ll_acc += log(ll_prod);
-                ll_prod = 1.0;
-            }
-            __syncthreads();   // Z and Q are rewritten by the next tile
+            ll_acc += log(ll_prod);
         }
 
-        // log-likelihood partial of the chunk: fixed butterfly inside the warp, fixed order across warps
+        // log-likelihood sum of the tile: fixed butterfly inside the warp, fixed order across warps
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) ll_acc += __shfl_xor_sync(0xffffffffu, ll_acc, off);
         if (lane == 0) wl[warp] = ll_acc;
-        __syncthreads();
-        double* out = p.partials + static_cast<long long>(chunk) * p.sv + (p.sv - 8);
-        if (tid == 0) out[0] = (wl[0] + wl[1]) + (wl[2] + wl[3]);
-        if (tid >= 1 && tid < 8) out[tid] = 0.0;
+        __syncthreads();   // also: Z and Q are rewritten by the next item
+        if (tid == 0) p.ll_tile[item] = (wl[0] + wl[1]) + (wl[2] + wl[3]);
     }
 }
 
@@ -392,6 +392,15 @@ __global__ void __launch_bounds__(kSpThreads, (NW * MW > 32) ? 1 : 2) em_split_m
         }
 
         double* out = p.partials + static_cast<long long>(chunk) * p.sv;
+        if (slab == 0 && cg == 0 && tid < 8) {
+            // the chunk's log-likelihood partial: its tiles' sums (E kernel) added in tile order
+            double ll = 0.0;
+            if (tid == 0) {
+                const int tpc = p.chunk / kSpTile;
+                for (int t = 0; t < tpc; ++t) ll += p.ll_tile[static_cast<long long>(chunk) * tpc + t];
+            }
+            out[p.sv - 8 + tid] = ll;
+        }
 #pragma unroll
         for (int i = 0; i < MW; ++i) {
             const int mt = (slab * 4 + warp) * MW + i;
