@@ -112,6 +112,21 @@ int mlb_data_download(mlb_data* data, int64_t begin, int64_t count, double* out)
 int mlb_data_shape(const mlb_data* data, int64_t* n_total, int64_t* n_local, int* d);
 int mlb_data_free(mlb_data* data);
 
+/* ---------------------------------------------------------------- initialisers (ML/Clustering.cpp) */
+
+/* The distance pass of KPP::init (Clustering.cpp:42-51), kept incrementally: a per-point vector `nearest`
+ * (squared distance to the nearest centroid chosen so far) stays resident next to the points and
+ *     nearest_i <- min(nearest_i, (x_i - centroid).squaredNorm())
+ * is applied for the newest centroid (D doubles); `first` != 0 starts from +infinity, i.e. leaves the plain
+ * squared distance to this centroid.  The values equal the ones the reference recomputes from scratch over
+ * all chosen centroids (a minimum does not depend on the order), at O(N D) per new centroid instead of
+ * O(N n D).  nearest_out (may be NULL: the pass is then only enqueued) receives the vector: n_total
+ * doubles, or the rank's own range in a rank context.  The draw itself (std::discrete_distribution over these weights, Clustering.cpp:55-56)
+ * stays on the host so that the caller's PRNG stream is the reference's. */
+int mlb_data_kpp_update(mlb_data* data, const double* centroid, int first, double* nearest_out);
+/* Number of kernels the library launched on this object after its creation (the seeding passes). */
+int mlb_data_launch_count(const mlb_data* data, int64_t* launches);
+
 /* ---------------------------------------------------------------- Gaussian-mixture EM (ML/EM.cpp) */
 
 int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out);
@@ -128,6 +143,12 @@ int mlb_em_set_params(mlb_em* em, const double* means, const double* covariances
  * contexts pass their own rows, n_local x K with leading dimension n_local) — the
  * `maximise_first` start (EM.cpp:120-125). */
 int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t ld);
+
+/* The same from hard assignments (n_total labels in [0, K), or the rank's own range): the M-step of the
+ * one-hot responsibilities ClosestCentroid::init writes (Clustering.cpp:72-89, `maximise_first` start),
+ * without the N x K host matrix.  The labels are what mlb_km_assign / mlb_km_get_labels give for the
+ * initial centroids (same strict <, lowest index wins). */
+int mlb_em_mstep_from_labels(mlb_em* em, const unsigned int* labels);
 
 /* One iteration of the hot loop (EM.cpp:143-147): expectation_step with the current theta_t, then
  * maximisation_step, fused on the device.  Returns the log-likelihood of theta_t (mean per point,
@@ -155,6 +176,12 @@ int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_o
 /* The same for the GLOBAL point range [begin, begin + count) only (resp_out is count x K with leading
  * dimension ld, labels_out has count entries).  Rank contexts can only emit rows they hold. */
 int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out, int64_t ld, unsigned int* labels_out);
+
+/* EM::assign_responsibilities (EM.cpp:176-188) for m points at once, with the CURRENT parameters (after a
+ * fit: the post-fit ones, as in the reference): x is column-major D x m with outer stride ld_x >= D, on
+ * the host; resp_out (may be NULL) is m x K column-major with leading dimension ld_out >= m; labels_out
+ * (may be NULL) is the argmax of each row (first maximum wins).  Runs on the first local GPU. */
+int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double* resp_out, int64_t ld_out, unsigned int* labels_out);
 
 /* Per-launch device timing of the dominant kernel (the fused E+M kernel) for roofline reports:
  * CUDA events recorded on the launching stream around each launch while enabled (at most 4096
@@ -187,6 +214,12 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed);
  * (an empty cluster goes to the origin), old centroids kept; returns ||C - C_old||_F^2
  * (KMeans.cpp:103). */
 int mlb_km_update(mlb_km* km, double* centroid_shift_sq);
+
+/* KMeans::assign_label (KMeans.cpp:153-165) for m points at once with the current centroids: x is
+ * column-major D x m with outer stride ld_x >= D, on the host; labels_out[i] is the nearest centroid
+ * (strict <, lowest index wins), sqdist_out[i] (may be NULL) its squared distance (x - c).squaredNorm().
+ * Does not touch the labels, statistics or centroids of the fit.  Runs on the first local GPU. */
+int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigned int* labels_out, double* sqdist_out);
 
 /* labels_ of the last assignment; rank contexts receive their own range. */
 int mlb_km_get_labels(mlb_km* km, unsigned int* labels);

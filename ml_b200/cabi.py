@@ -47,17 +47,21 @@ SIGNATURES = {
     "mlb_data_download": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),
     "mlb_data_shape": (ctypes.c_int, [_vp, _c_i64p, _c_i64p, _c_ip]),
     "mlb_data_free": (ctypes.c_int, [_vp]),
+    "mlb_data_kpp_update": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
+    "mlb_data_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
     "mlb_em_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
     "mlb_em_destroy": (ctypes.c_int, [_vp]),
     "mlb_em_sample_covariance": (ctypes.c_int, [_vp, _vp]),
     "mlb_em_set_params": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "mlb_em_mstep_from_responsibilities": (ctypes.c_int, [_vp, _vp, ctypes.c_int64]),
+    "mlb_em_mstep_from_labels": (ctypes.c_int, [_vp, _vp]),
     "mlb_em_step": (ctypes.c_int, [_vp, _c_dp]),
     "mlb_em_run_steps": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "mlb_em_get_params": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "mlb_em_get_precisions": (ctypes.c_int, [_vp, _vp, _vp]),
     "mlb_em_emit": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     "mlb_em_emit_range": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int64, _vp]),
+    "mlb_em_predict": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, _vp, ctypes.c_int64, _vp]),
     "mlb_em_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "mlb_em_kernel_time_ms": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
     "mlb_em_last_path": (ctypes.c_int, [_vp, _c_ip]),
@@ -68,6 +72,7 @@ SIGNATURES = {
     "mlb_km_get_centroids": (ctypes.c_int, [_vp, _vp]),
     "mlb_km_assign": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
     "mlb_km_update": (ctypes.c_int, [_vp, _c_dp]),
+    "mlb_km_predict": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, _vp, _vp]),
     "mlb_km_get_labels": (ctypes.c_int, [_vp, _vp]),
     "mlb_km_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
     "mlb_km_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
@@ -229,6 +234,22 @@ class Data:
         check(lib().mlb_data_download(self._h, begin, count, _ptr(out)))
         return out
 
+    def kpp_update(self, centroid, first, want_nearest=True):
+        """The distance pass of KPP::init (Clustering.cpp:42-51) for the newest centroid; returns the per-point
+        squared distance to the nearest centroid chosen so far (all held points), or None."""
+        c = np.ascontiguousarray(centroid, dtype=np.float64)
+        _, n_local, d = self.shape
+        assert c.shape == (d,)
+        out = np.empty(n_local) if want_nearest else None
+        check(lib().mlb_data_kpp_update(self._h, _ptr(c), int(bool(first)), _ptr(out)))
+        return out
+
+    @property
+    def launch_count(self):
+        c = ctypes.c_int64()
+        check(lib().mlb_data_launch_count(self._h, ctypes.byref(c)))
+        return c.value
+
     def close(self):
         if self._h:
             lib().mlb_data_free(self._h)
@@ -268,6 +289,22 @@ class Em:
         """resp_nk: (n, K) responsibilities as ml::EM::responsibilities() (column-major N x K)."""
         r = np.asfortranarray(resp_nk, dtype=np.float64)
         check(lib().mlb_em_mstep_from_responsibilities(self._h, _ptr(r), r.shape[0]))
+
+    def mstep_from_labels(self, labels):
+        """The M-step of one-hot responsibilities (ClosestCentroid start, Clustering.cpp:72-89) from the labels."""
+        lab = np.ascontiguousarray(labels, dtype=np.uint32)
+        assert lab.shape == (self.n_local,)
+        check(lib().mlb_em_mstep_from_labels(self._h, _ptr(lab)))
+
+    def predict(self, points, want_responsibilities=True, want_labels=True):
+        """EM::assign_responsibilities (EM.cpp:176-188) for the rows of `points` (m, D) with the current parameters."""
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        assert pts.ndim == 2 and pts.shape[1] == self.d
+        m = pts.shape[0]
+        resp = np.empty((m, self.k), order="F") if want_responsibilities else None
+        labels = np.empty(m, dtype=np.uint32) if want_labels else None
+        check(lib().mlb_em_predict(self._h, _ptr(pts), m, self.d, _ptr(resp), max(m, 1), _ptr(labels)))
+        return resp, labels
 
     def step(self):
         ll = ctypes.c_double()
@@ -361,6 +398,16 @@ class Km:
         shift = ctypes.c_double()
         check(lib().mlb_km_update(self._h, ctypes.byref(shift)))
         return shift.value
+
+    def predict(self, points):
+        """KMeans::assign_label (KMeans.cpp:153-165) for the rows of `points` (m, D): (labels, squared distances)."""
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        assert pts.ndim == 2 and pts.shape[1] == self.d
+        m = pts.shape[0]
+        labels = np.empty(m, dtype=np.uint32)
+        dist = np.empty(m)
+        check(lib().mlb_km_predict(self._h, _ptr(pts), m, self.d, _ptr(labels), _ptr(dist)))
+        return labels, dist
 
     def get_labels(self):
         labels = np.empty(self.n_local, dtype=np.uint32)

@@ -636,6 +636,8 @@ int mlb_data_free(mlb_data* data)
         if (data->shards[g].owned && data->shards[g].x) cudaFreeAsync(data->shards[g].x, data->ctx->gpus[g].stream);
         if (data->shards[g].shift) cudaFreeAsync(data->shards[g].shift, data->ctx->gpus[g].stream);
         if (data->shards[g].reduce_scratch) cudaFreeAsync(data->shards[g].reduce_scratch, data->ctx->gpus[g].stream);
+        if (data->shards[g].nearest) cudaFreeAsync(data->shards[g].nearest, data->ctx->gpus[g].stream);
+        if (data->shards[g].seed_centroid) cudaFreeAsync(data->shards[g].seed_centroid, data->ctx->gpus[g].stream);
     }
     delete data;
     return MLB_OK;

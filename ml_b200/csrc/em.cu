@@ -1101,21 +1101,11 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
     return MLB_OK;
 }
 
-int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t ld)
+// maximisation_step from responsibilities already on the devices: dev[g] is column-major, local rows of GPU g, leading
+// dimension max(1, n_local).  Frees the buffers.
+static int mstep_from_device(mlb_em* em, std::vector<double*>& dev, int rc)
 {
-    MLB_REQUIRE(em && resp, "mlb_em_mstep_from_responsibilities: null argument");
     mlb_ctx* ctx = em->ctx;
-    const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
-    std::vector<double*> dev(ctx->gpus.size(), nullptr);
-    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
-        const DataShard& sh = em->data->shards[g];
-        const int64_t n = std::max<int64_t>(1, sh.n());
-        MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
-        if (sh.n() > 0)
-            MLB_CUDA(cudaMemcpy2DAsync(dev[g], sizeof(double) * n, resp + (sh.begin - host_begin), sizeof(double) * ld, sizeof(double) * sh.n(),
-                                       em->k, cudaMemcpyHostToDevice, gpu.stream));
-        return MLB_OK;
-    });
     if (rc == MLB_OK) {
         rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int {
             const int64_t n = em->data->shards[g].n();
@@ -1146,6 +1136,65 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
         if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(dev[g], ctx->gpus[g].stream); }
     if (rc == MLB_OK) { em->have_params = true; em->have_step = false; }
     return rc;
+}
+
+// One-hot responsibilities (Clustering.cpp:76,87) from labels: r[i + k * ld] = (labels[i] == k).
+__global__ void em_onehot_kernel(const unsigned* __restrict__ labels, long long n, int k, double* __restrict__ r)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned label = labels[i];
+    for (int kk = 0; kk < k; ++kk) r[i + static_cast<long long>(kk) * n] = label == static_cast<unsigned>(kk) ? 1.0 : 0.0;
+}
+
+int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t ld)
+{
+    MLB_REQUIRE(em && resp, "mlb_em_mstep_from_responsibilities: null argument");
+    mlb_ctx* ctx = em->ctx;
+    const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
+    std::vector<double*> dev(ctx->gpus.size(), nullptr);
+    const int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        const DataShard& sh = em->data->shards[g];
+        const int64_t n = std::max<int64_t>(1, sh.n());
+        MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
+        if (sh.n() > 0)
+            MLB_CUDA(cudaMemcpy2DAsync(dev[g], sizeof(double) * n, resp + (sh.begin - host_begin), sizeof(double) * ld, sizeof(double) * sh.n(),
+                                       em->k, cudaMemcpyHostToDevice, gpu.stream));
+        return MLB_OK;
+    });
+    return mstep_from_device(em, dev, rc);
+}
+
+int mlb_em_mstep_from_labels(mlb_em* em, const unsigned int* labels)
+{
+    MLB_REQUIRE(em && labels, "mlb_em_mstep_from_labels: null argument");
+    mlb_ctx* ctx = em->ctx;
+    const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
+    {
+        // a label outside [0, K) would silently drop its point from every component
+        int64_t n_held = 0;
+        for (const DataShard& sh : em->data->shards) n_held += sh.n();
+        for (int64_t i = 0; i < n_held; ++i)
+            MLB_REQUIRE(labels[i] < static_cast<unsigned>(em->k), "mlb_em_mstep_from_labels: label %u of point %lld out of range", labels[i], static_cast<long long>(i + host_begin));
+    }
+    std::vector<double*> dev(ctx->gpus.size(), nullptr);
+    std::vector<unsigned*> dev_labels(ctx->gpus.size(), nullptr);
+    const int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        const DataShard& sh = em->data->shards[g];
+        const int64_t n = std::max<int64_t>(1, sh.n());
+        MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&dev_labels[g], sizeof(unsigned) * n, gpu.stream));
+        if (sh.n() > 0) {
+            MLB_CUDA(cudaMemcpyAsync(dev_labels[g], labels + (sh.begin - host_begin), sizeof(unsigned) * sh.n(), cudaMemcpyHostToDevice, gpu.stream));
+            em_onehot_kernel<<<static_cast<unsigned>((sh.n() + 255) / 256), 256, 0, gpu.stream>>>(dev_labels[g], sh.n(), em->k, dev[g]);
+            MLB_CUDA(cudaGetLastError());
+            ++em->launches;
+        }
+        return MLB_OK;
+    });
+    for (size_t g = 0; g < dev_labels.size(); ++g)
+        if (dev_labels[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(dev_labels[g], ctx->gpus[g].stream); }
+    return mstep_from_device(em, dev, rc);
 }
 
 int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out, int64_t ld, unsigned int* labels_out)
@@ -1216,6 +1265,83 @@ int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_o
     MLB_REQUIRE(em, "mlb_em_emit: null argument");
     const std::vector<DataShard>& shards = em->data->shards;
     return mlb_em_emit_range(em, shards.front().begin, shards.back().end - shards.front().begin, resp_out, ld, labels_out);
+}
+
+int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double* resp_out, int64_t ld_out, unsigned int* labels_out)
+{
+    MLB_REQUIRE(em && x, "mlb_em_predict: null argument");
+    MLB_REQUIRE(m >= 0 && ld_x >= em->d, "mlb_em_predict: bad shape (m=%lld, ld_x=%lld, D=%d)", static_cast<long long>(m), static_cast<long long>(ld_x), em->d);
+    MLB_REQUIRE(!resp_out || ld_out >= m, "mlb_em_predict: leading dimension smaller than the row count");
+    if (!em->have_params) { set_error("mlb_em_predict: parameters not set"); return MLB_ESTATE; }
+    if (m == 0 || (!resp_out && !labels_out)) return MLB_OK;
+    mlb_ctx* ctx = em->ctx;
+    Gpu& gpu = ctx->gpus[0];
+    EmGpu& eg = em->gpus[0];
+    const int d = em->d;
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    if (resp_out && !eg.stage) MLB_CUDA(cudaMallocAsync(&eg.stage, sizeof(double) * kStagePoints * em->k, gpu.stream));
+    if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMallocAsync(&eg.stage_labels, sizeof(unsigned) * kStagePoints, gpu.stream));
+    const int64_t cap = std::min<int64_t>(m, kStagePoints);
+    double *xd = nullptr, *r_tmp = nullptr, *ll_tmp = nullptr;
+    MLB_CUDA(cudaMallocAsync(&xd, sizeof(double) * cap * d, gpu.stream));
+    int rc = MLB_OK;
+    auto body = [&]() -> int {
+        if (em->path == 2) {
+            MLB_CUDA(cudaMallocAsync(&r_tmp, sizeof(double) * cap * em->KP, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&ll_tmp, sizeof(double) * ((cap + 127) / 128) * 2, gpu.stream));
+        }
+        for (int64_t off = 0; off < m; off += kStagePoints) {
+            const int64_t n = std::min<int64_t>(kStagePoints, m - off);
+            const double* src = x + off * ld_x;
+            if (ld_x == d) MLB_CUDA(cudaMemcpyAsync(xd, src, sizeof(double) * n * d, cudaMemcpyHostToDevice, gpu.stream));
+            else MLB_CUDA(cudaMemcpy2DAsync(xd, sizeof(double) * d, src, sizeof(double) * ld_x, sizeof(double) * d, n, cudaMemcpyHostToDevice, gpu.stream));
+            if (em->path == 2) {
+                // E kernel on the staged points (responsibilities into r_tmp), then the transposing emit kernel
+                EmSplitArgs a = split_args(em, 0, eg.theta[em->cur]);
+                a.x = xd;
+                a.n_local = n;
+                a.chunk = 128;
+                a.n_chunks = static_cast<int>((n + 127) / 128);
+                a.r = r_tmp;
+                a.ll_tile = ll_tmp;
+                MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
+                const long long e_items = static_cast<long long>(a.n_chunks) * (a.chunk / kSpTile);
+                em->fn_split_e<<<static_cast<unsigned>(std::min<long long>(eg.grid_e, e_items)), kSpThreads, em->smem_split_e, gpu.stream>>>(a);
+                MLB_CUDA(cudaGetLastError());
+                a.range_begin = 0;
+                a.range_count = n;
+                a.r_out = resp_out ? eg.stage : nullptr;
+                a.r_out_ld = kStagePoints;
+                a.labels_out = labels_out ? eg.stage_labels : nullptr;
+                em_split_emit_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, gpu.stream>>>(a);
+                MLB_CUDA(cudaGetLastError());
+                em->launches += 2;
+            } else {
+                EmArgs a = base_args(em, 0);
+                a.x = xd;
+                a.n_local = n;
+                a.theta = eg.theta[em->cur];   // the current parameters (EM.cpp:176-188 uses the post-fit ones)
+                a.chunk = kTile;
+                a.n_chunks = static_cast<int>((n + kTile - 1) / kTile);
+                a.range_begin = 0;
+                a.range_count = n;
+                a.r_out = resp_out ? eg.stage : nullptr;
+                a.r_out_ld = kStagePoints;
+                a.labels_out = labels_out ? eg.stage_labels : nullptr;
+                MLB_TRY(launch_em(em, em->fn_emit, a, 0, 8 * kSmCount));
+            }
+            if (resp_out)
+                for (int kk = 0; kk < em->k; ++kk)
+                    MLB_TRY(staged_d2h(gpu, resp_out + off + static_cast<int64_t>(kk) * ld_out, eg.stage + static_cast<int64_t>(kk) * kStagePoints, sizeof(double) * n));
+            if (labels_out) MLB_TRY(staged_d2h(gpu, labels_out + off, eg.stage_labels, sizeof(unsigned) * n));
+            MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        }
+        return MLB_OK;
+    };
+    rc = body();
+    for (double* ptr : {xd, r_tmp, ll_tmp})
+        if (ptr) cudaFreeAsync(ptr, gpu.stream);
+    return rc;
 }
 
 int mlb_em_set_kernel_timing(mlb_em* em, int enabled)

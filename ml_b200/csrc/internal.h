@@ -125,6 +125,8 @@ struct DataShard {
     double* shift = nullptr;   // d doubles: the global data mean (device copy)
     double* reduce_scratch = nullptr;  // level-1 group sums of reduce_and_exchange (grown on demand)
     size_t reduce_scratch_len = 0;
+    double* nearest = nullptr;        // K-means++ seeding: squared distance to the nearest chosen centroid, per local point (seeding.cu)
+    double* seed_centroid = nullptr;  // d doubles: the newest centroid of the seeding pass
     int64_t n() const { return end - begin; }
     int64_t n_chunks() const { return chunk_end - chunk_begin; }
 };
@@ -137,6 +139,7 @@ struct mlb_data {
     int d = 0;
     std::vector<mlb::DataShard> shards;  // one per local GPU
     std::vector<double> shift;           // host copy of the global data mean
+    int64_t launches = 0;                // kernels launched on this object after its creation (seeding passes)
 };
 
 namespace mlb {

@@ -41,6 +41,7 @@ struct KmArgs {
     double* partials;       // [n_chunks][SV]: K x (D+1) sums and counts, inertia, changed
     int chunk, n_chunks;
     unsigned* counter;
+    double* dist_out;       // optional: the squared distance of every point to its centroid (mlb_km_predict)
 };
 
 __device__ __forceinline__ void km_dmma(double (&acc)[2], double a, double b)
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
                     inertia_acc += d2;
                     if (old_labels[pl] != static_cast<unsigned>(label)) ++changed_acc;
                     p.labels[tile0 + pl] = static_cast<unsigned>(label);
+                    if (p.dist_out) p.dist_out[tile0 + pl] = d2;
                 }
             }
             __syncwarp();   // the buffer and the verdicts are rewritten two sub-tiles later / by the next sub-tile
@@ -863,6 +865,55 @@ int mlb_km_update(mlb_km* km, double* centroid_shift_sq)
     if (centroid_shift_sq) *centroid_shift_sq = host;
     km->have_stats = false;
     return MLB_OK;
+}
+
+int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigned int* labels_out, double* sqdist_out)
+{
+    MLB_REQUIRE(km && x && labels_out, "mlb_km_predict: null argument");
+    MLB_REQUIRE(m >= 0 && ld_x >= km->d, "mlb_km_predict: bad shape (m=%lld, ld_x=%lld, D=%d)", static_cast<long long>(m), static_cast<long long>(ld_x), km->d);
+    if (!km->have_centroids) { set_error("mlb_km_predict: centroids not set"); return MLB_ESTATE; }
+    if (m == 0) return MLB_OK;
+    constexpr int64_t kStage = 1 << 20;   // points per staged batch
+    constexpr int kChunk = 2048;          // the assignment kernel writes one (unused here) inertia partial per chunk
+    Gpu& gpu = km->ctx->gpus[0];
+    KmGpu& kg = km->gpus[0];
+    const int d = km->d;
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    const int64_t cap = std::min<int64_t>(m, kStage);
+    double *xd = nullptr, *dist = nullptr, *partials = nullptr;
+    unsigned* labels = nullptr;
+    auto body = [&]() -> int {
+        MLB_CUDA(cudaMallocAsync(&xd, sizeof(double) * cap * d, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&dist, sizeof(double) * cap, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&labels, sizeof(unsigned) * cap, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&partials, sizeof(double) * ((cap + kChunk - 1) / kChunk) * km->SV, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(labels, 0, sizeof(unsigned) * cap, gpu.stream));   // the kernel reads the "previous" labels
+        for (int64_t off = 0; off < m; off += kStage) {
+            const int64_t n = std::min<int64_t>(kStage, m - off);
+            const double* src = x + off * ld_x;
+            if (ld_x == d) MLB_CUDA(cudaMemcpyAsync(xd, src, sizeof(double) * n * d, cudaMemcpyHostToDevice, gpu.stream));
+            else MLB_CUDA(cudaMemcpy2DAsync(xd, sizeof(double) * d, src, sizeof(double) * ld_x, sizeof(double) * d, n, cudaMemcpyHostToDevice, gpu.stream));
+            KmArgs a{};
+            a.x = xd; a.n_local = n; a.d = d; a.k = km->k; a.KP = km->KP;
+            a.shift = km->data->shards[0].shift; a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
+            a.labels = labels; a.partials = partials;
+            a.chunk = kChunk; a.n_chunks = static_cast<int>((n + kChunk - 1) / kChunk);
+            a.counter = kg.counter;
+            a.dist_out = dist;
+            MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+            km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+            MLB_CUDA(cudaGetLastError());
+            ++km->launches;
+            MLB_TRY(staged_d2h(gpu, labels_out + off, labels, sizeof(unsigned) * n));
+            if (sqdist_out) MLB_TRY(staged_d2h(gpu, sqdist_out + off, dist, sizeof(double) * n));
+            MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        }
+        return MLB_OK;
+    };
+    const int rc = body();
+    for (void* ptr : {static_cast<void*>(xd), static_cast<void*>(dist), static_cast<void*>(labels), static_cast<void*>(partials)})
+        if (ptr) cudaFreeAsync(ptr, gpu.stream);
+    return rc;
 }
 
 int mlb_km_get_labels(mlb_km* km, unsigned int* labels)

@@ -90,6 +90,12 @@ namespace ml
 			DLL_DECLSPEC ClosestCentroid(std::shared_ptr<const CentroidsInitialiser> centroids_initialiser);
 
 			DLL_DECLSPEC void init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> responsibilities) const override;
+
+			/** The initialiser the centroids come from (an addition: lets ml::EM run the nearest-centroid pass on the device). */
+			const std::shared_ptr<const CentroidsInitialiser>& centroids_initialiser() const
+			{
+				return centroids_initialiser_;
+			}
 		private:
 			std::shared_ptr<const CentroidsInitialiser> centroids_initialiser_;
 		};

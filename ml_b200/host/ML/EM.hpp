@@ -8,6 +8,9 @@
 // Differences from the reference header, all additive:
 //   - number_iterations(): iterations run by the last fit (requested by the north star; the
 //     reference does not store it);
+//   - assign_responsibilities(points): the batched form of assign_responsibilities(x, u), on the device;
+//   - the built-in KPP and ClosestCentroid initialisers run their O(N K D) distance passes on the device (the draws
+//     stay on the host with the model's PRNG, so the initial state is the reference's);
 //   - responsibilities() is out of line: the N x K matrix stays on the device until first asked for
 //     (25.6 GB at N=1e8, K=32), then is materialised once; the values are the reference's.
 #include <memory>
@@ -112,6 +115,11 @@ namespace ml
 		@throw std::invalid_argument On size mismatch. */
 		DLL_DECLSPEC void assign_responsibilities(Eigen::Ref<const Eigen::VectorXd> x, Eigen::Ref<Eigen::VectorXd> u) const;
 
+		/** The same for every column of `points` (D x m) at once, on the device: m x K.
+		@throw std::invalid_argument If `points` has the wrong number of rows.
+		@throw std::logic_error If there is no fitted device state (no fit yet, or the N == K exact fit). */
+		DLL_DECLSPEC Eigen::MatrixXd assign_responsibilities(Eigen::Ref<const Eigen::MatrixXd> points) const;
+
 		const std::vector<unsigned int>& labels() const override
 		{
 			return labels_;
@@ -150,6 +158,7 @@ namespace ml
 		bool converged_;
 		mutable std::unique_ptr<detail::EmDevice> device_; /**< HBM-resident state of the last fit */
 
+		void initialise_centroids(const Clustering::CentroidsInitialiser& initialiser, Eigen::Ref<const Eigen::MatrixXd> data, Eigen::Ref<Eigen::MatrixXd> centroids);
 		void process_covariances(Eigen::Index number_dimensions);
 		void fetch_parameters(Eigen::Index number_dimensions);
 	};

@@ -1,6 +1,7 @@
 #pragma once
 // ml::Clustering::KMeans: Lloyd's algorithm with the reference's public surface
-// (ML/KMeans.hpp:19-101) on the B200 backend; number_iterations() is the one addition.
+// (ML/KMeans.hpp:19-101) on the B200 backend.  Additions: number_iterations(), and assign_labels(points), the
+// batched form of assign_label(x) on the device.
 #include "Clustering.hpp"
 #include <memory>
 #include <vector>
@@ -64,6 +65,11 @@ namespace ml
             @throw std::invalid_argument If x has the wrong size. */
             DLL_DECLSPEC std::pair<unsigned int, double> assign_label(Eigen::Ref<const Eigen::VectorXd> x) const;
 
+            /** The same for every column of `points` (D x m) at once, on the device.
+            @throw std::invalid_argument If `points` has the wrong number of rows.
+            @throw std::logic_error If there is no fitted device state (no fit yet, or the N == K exact fit). */
+            DLL_DECLSPEC std::pair<std::vector<unsigned int>, std::vector<double>> assign_labels(Eigen::Ref<const Eigen::MatrixXd> points) const;
+
             /** Sum of squared distances of the points to their centroids. */
             double inertia() const
             {
@@ -93,6 +99,7 @@ namespace ml
             unsigned int number_iterations_;
             bool verbose_;
             bool converged_;
+            mutable std::unique_ptr<detail::KmDevice> device_; /**< HBM-resident state of the last fit */
 
             bool fit_once(Eigen::Ref<const Eigen::MatrixXd> data, detail::KmDevice& device);
         };

@@ -27,7 +27,7 @@ namespace
 	Eigen::Map<const Eigen::MatrixXd> as_columns(const py::array& data)
 	{
 		if (!py::isinstance<py::array_t<double>>(data) || data.ndim() != 2 || !(data.flags() & py::array::c_style)) {
-			throw py::type_error("fit(): incompatible function arguments. data must be a C-contiguous float64 numpy array of shape (N, D); no conversion is performed");
+			throw py::type_error("incompatible function arguments. data must be a C-contiguous float64 numpy array of shape (N, D); no conversion is performed");
 		}
 		return Eigen::Map<const Eigen::MatrixXd>(static_cast<const double*>(data.data()), data.shape(1), data.shape(0));
 	}
@@ -82,6 +82,18 @@ namespace ml
 			EM::assign_responsibilities(point, u);
 			return to_numpy(u);
 		}
+
+		/** (m, D) points -> (m, K) responsibilities, on the device. */
+		py::array_t<double> calculate_responsibilities_batch(const py::array& points) const
+		{
+			const auto columns = as_columns(points);
+			Eigen::MatrixXd result;
+			{
+				py::gil_scoped_release release;
+				result = EM::assign_responsibilities(columns);
+			}
+			return to_numpy(result);
+		}
 	};
 
 	namespace Clustering
@@ -113,6 +125,22 @@ namespace ml
 			std::pair<unsigned int, double> assign_label_py(const py::array_t<double, py::array::c_style | py::array::forcecast>& x) const
 			{
 				return assign_label(as_vector(x));
+			}
+
+			/** (m, D) points -> (labels uint32 (m,), squared distances (m,)), on the device. */
+			std::pair<py::array_t<unsigned int>, py::array_t<double>> assign_labels_py(const py::array& points) const
+			{
+				const auto columns = as_columns(points);
+				std::pair<std::vector<unsigned int>, std::vector<double>> result;
+				{
+					py::gil_scoped_release release;
+					result = assign_labels(columns);
+				}
+				py::array_t<unsigned int> labels(static_cast<py::ssize_t>(result.first.size()));
+				py::array_t<double> distances(static_cast<py::ssize_t>(result.second.size()));
+				std::memcpy(labels.mutable_data(), result.first.data(), sizeof(unsigned int) * result.first.size());
+				std::memcpy(distances.mutable_data(), result.second.data(), sizeof(double) * result.second.size());
+				return std::make_pair(labels, distances);
 			}
 		};
 	}
@@ -166,6 +194,8 @@ void init_clustering(py::module_& m)
 			"Returns k-th covariance matrix.\n\nArgs:\n    k: Component index.\n\nReturns:\n    2D square matrix.")
 		.def("assign_responsibilities", &ml::EMPy::calculate_responsibilities, py::arg("x"),
 			"Given a data point x, calculate each component's responsibilities for x and return them.\n\nArgs:\n    x: Data point with correct number of dimensions.\n\nReturns:\n    1D array of responsibilities.")
+		.def("assign_responsibilities_batch", &ml::EMPy::calculate_responsibilities_batch, py::arg("data").noconvert(),
+			"Responsibilities of the fitted components for every row of data (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    2D array, one row of responsibilities per data point.")
 		.doc() = "Gaussian Expectation-Maximisation algorithm.";
 
 	py::class_<ml::Clustering::KMeansPy, std::shared_ptr<ml::Clustering::KMeansPy>>(m_clustering, "KMeans")
@@ -186,5 +216,7 @@ void init_clustering(py::module_& m)
 		.def_property_readonly("number_iterations", &ml::Clustering::KMeansPy::number_iterations, "Assignment steps run by the last fit.")
 		.def("assign_label", &ml::Clustering::KMeansPy::assign_label_py, py::arg("x"),
 			"Given a data point x, assigns it to the closest cluster.\n\nArgs:\n    x: Data point with correct number of dimensions.\n\nReturns:\n    Tuple of cluster label and squared Euclidean distance to cluster centroid.")
+		.def("assign_labels", &ml::Clustering::KMeansPy::assign_labels_py, py::arg("data").noconvert(),
+			"Assigns every row of data to its closest cluster (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    Tuple of the array of cluster labels and the array of squared Euclidean distances to the cluster centroids.")
 		.doc() = "K-means clustering algorithm.";
 }

@@ -1,5 +1,6 @@
 #include "Backend.hpp"
 
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <stdexcept>
@@ -61,10 +62,32 @@ namespace ml
 			mlb_data_free(handle_);
 		}
 
-		EmDevice::EmDevice(Eigen::Ref<const Eigen::MatrixXd> data, unsigned int number_components)
-			: data_(data), number_components_(number_components)
+		void DeviceData::kpp_update(const double* centroid, bool first, std::vector<double>& nearest)
 		{
-			check(mlb_em_create(shared_context(), data_.handle(), static_cast<int>(number_components), &em_), "EM");
+			nearest.resize(static_cast<size_t>(cols_));
+			check(mlb_data_kpp_update(handle_, centroid, first ? 1 : 0, nearest.data()), "KPP distance pass");
+		}
+
+		void kpp_on_device(DeviceData& device_data, Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, const unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids)
+		{
+			const Eigen::Index dim = data.rows();
+			std::vector<double> weights(static_cast<size_t>(data.cols()), 1.0);   // first draw: uniform (Clustering.cpp:53)
+			std::vector<double> newest(static_cast<size_t>(dim));
+			for (unsigned int k = 0; k < number_components; ++k) {
+				if (k > 0) {
+					device_data.kpp_update(newest.data(), k == 1, weights);
+				}
+				std::discrete_distribution<Eigen::Index> draw(weights.begin(), weights.end());
+				const Eigen::Index index = draw(prng);
+				std::copy_n(data.data() + index * data.outerStride(), dim, newest.begin());
+				std::copy_n(newest.begin(), dim, centroids.data() + static_cast<Eigen::Index>(k) * centroids.outerStride());
+			}
+		}
+
+		EmDevice::EmDevice(Eigen::Ref<const Eigen::MatrixXd> data, unsigned int number_components)
+			: data_(std::make_shared<DeviceData>(data)), number_components_(number_components)
+		{
+			check(mlb_em_create(shared_context(), data_->handle(), static_cast<int>(number_components), &em_), "EM");
 		}
 
 		EmDevice::~EmDevice()
@@ -74,14 +97,14 @@ namespace ml
 
 		Eigen::MatrixXd EmDevice::sample_covariance()
 		{
-			Eigen::MatrixXd covariance(data_.rows(), data_.rows());
+			Eigen::MatrixXd covariance(data_->rows(), data_->rows());
 			check(mlb_em_sample_covariance(em_, covariance.data()), "EM sample covariance");
 			return covariance;
 		}
 
 		void EmDevice::set_parameters(const Eigen::MatrixXd& means, const std::vector<Eigen::MatrixXd>& covariances, const Eigen::VectorXd& mixing_probabilities)
 		{
-			const auto dd = static_cast<size_t>(data_.rows() * data_.rows());
+			const auto dd = static_cast<size_t>(data_->rows() * data_->rows());
 			std::vector<double> packed(dd * covariances.size());
 			for (size_t k = 0; k < covariances.size(); ++k) {
 				std::copy(covariances[k].data(), covariances[k].data() + dd, packed.begin() + static_cast<std::ptrdiff_t>(k * dd));
@@ -94,6 +117,20 @@ namespace ml
 			check(mlb_em_mstep_from_responsibilities(em_, responsibilities.data(), responsibilities.rows()), "EM maximisation step");
 		}
 
+		void EmDevice::maximise_from_labels(const std::vector<unsigned int>& labels)
+		{
+			if (static_cast<Eigen::Index>(labels.size()) != data_->cols()) {
+				throw std::invalid_argument("EM maximisation step: wrong number of labels");
+			}
+			check(mlb_em_mstep_from_labels(em_, labels.data()), "EM maximisation step");
+		}
+
+		void EmDevice::predict(Eigen::Ref<const Eigen::MatrixXd> points, Eigen::MatrixXd& responsibilities)
+		{
+			responsibilities.resize(points.cols(), number_components_);
+			check(mlb_em_predict(em_, points.data(), points.cols(), points.outerStride(), responsibilities.data(), std::max<Eigen::Index>(1, points.cols()), nullptr), "EM responsibilities of new points");
+		}
+
 		double EmDevice::step()
 		{
 			double log_likelihood = 0;
@@ -103,7 +140,7 @@ namespace ml
 
 		void EmDevice::get_parameters(Eigen::MatrixXd& means, std::vector<Eigen::MatrixXd>& covariances, Eigen::VectorXd& mixing_probabilities)
 		{
-			const Eigen::Index d = data_.rows();
+			const Eigen::Index d = data_->rows();
 			const auto dd = static_cast<size_t>(d * d);
 			std::vector<double> packed(dd * number_components_);
 			means.resize(d, number_components_);
@@ -119,12 +156,12 @@ namespace ml
 		void EmDevice::emit(Eigen::MatrixXd* responsibilities, std::vector<unsigned int>* labels)
 		{
 			if (responsibilities) {
-				responsibilities->resize(data_.cols(), number_components_);
+				responsibilities->resize(data_->cols(), number_components_);
 			}
 			if (labels) {
-				labels->resize(static_cast<size_t>(data_.cols()));
+				labels->resize(static_cast<size_t>(data_->cols()));
 			}
-			check(mlb_em_emit(em_, responsibilities ? responsibilities->data() : nullptr, data_.cols(), labels ? labels->data() : nullptr), "EM responsibilities");
+			check(mlb_em_emit(em_, responsibilities ? responsibilities->data() : nullptr, data_->cols(), labels ? labels->data() : nullptr), "EM responsibilities");
 		}
 
 		void EmDevice::emit_rows(Eigen::Index begin, Eigen::Index count, Eigen::MatrixXd& responsibilities)
@@ -134,9 +171,14 @@ namespace ml
 		}
 
 		KmDevice::KmDevice(Eigen::Ref<const Eigen::MatrixXd> data, unsigned int number_clusters)
-			: data_(data)
+			: KmDevice(std::make_shared<DeviceData>(data), number_clusters)
 		{
-			check(mlb_km_create(shared_context(), data_.handle(), static_cast<int>(number_clusters), &km_), "KMeans");
+		}
+
+		KmDevice::KmDevice(std::shared_ptr<DeviceData> data, unsigned int number_clusters)
+			: data_(std::move(data))
+		{
+			check(mlb_km_create(shared_context(), data_->handle(), static_cast<int>(number_clusters), &km_), "KMeans");
 		}
 
 		KmDevice::~KmDevice()
@@ -170,9 +212,16 @@ namespace ml
 			return shift;
 		}
 
+		void KmDevice::predict(Eigen::Ref<const Eigen::MatrixXd> points, std::vector<unsigned int>& labels, std::vector<double>& squared_distances)
+		{
+			labels.resize(static_cast<size_t>(points.cols()));
+			squared_distances.resize(static_cast<size_t>(points.cols()));
+			check(mlb_km_predict(km_, points.data(), points.cols(), points.outerStride(), labels.data(), squared_distances.data()), "KMeans labels of new points");
+		}
+
 		void KmDevice::get_labels(std::vector<unsigned int>& labels)
 		{
-			labels.resize(static_cast<size_t>(data_.cols()));
+			labels.resize(static_cast<size_t>(data_->cols()));
 			check(mlb_km_get_labels(km_, labels.data()), "KMeans labels");
 		}
 	}

@@ -3,6 +3,7 @@
 // process-wide GPU context, and the mapping of status codes to the exceptions the reference throws.
 #include <cstdint>
 #include <memory>
+#include <random>
 #include <vector>
 #include <Eigen/Core>
 
@@ -33,10 +34,17 @@ namespace ml
 			mlb_data* handle() const { return handle_; }
 			Eigen::Index rows() const { return rows_; }
 			Eigen::Index cols() const { return cols_; }
+			/** KPP distance pass for the newest centroid (D doubles); `nearest` (N) receives the squared distance of
+			every point to the nearest centroid chosen so far. */
+			void kpp_update(const double* centroid, bool first, std::vector<double>& nearest);
 		private:
 			mlb_data* handle_ = nullptr;
 			Eigen::Index rows_ = 0, cols_ = 0;
 		};
+
+		/** KPP::init (ML/Clustering.cpp:39-59) with the distance passes on the device and the draws on the host:
+		the same std::discrete_distribution over the same weights, so the same centroids and PRNG stream. */
+		void kpp_on_device(DeviceData& device_data, Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids);
 
 		/** Device state of one EM fit. */
 		class EmDevice
@@ -49,12 +57,17 @@ namespace ml
 			Eigen::MatrixXd sample_covariance();
 			void set_parameters(const Eigen::MatrixXd& means, const std::vector<Eigen::MatrixXd>& covariances, const Eigen::VectorXd& mixing_probabilities);
 			void maximise_from(const Eigen::MatrixXd& responsibilities);
+			/** M-step of the one-hot responsibilities of hard labels (ClosestCentroid start). */
+			void maximise_from_labels(const std::vector<unsigned int>& labels);
+			/** Responsibilities (m x K) of the columns of `points` (D x m) under the current parameters. */
+			void predict(Eigen::Ref<const Eigen::MatrixXd> points, Eigen::MatrixXd& responsibilities);
+			const std::shared_ptr<DeviceData>& data() const { return data_; }
 			double step();
 			void get_parameters(Eigen::MatrixXd& means, std::vector<Eigen::MatrixXd>& covariances, Eigen::VectorXd& mixing_probabilities);
 			void emit(Eigen::MatrixXd* responsibilities, std::vector<unsigned int>* labels);
 			void emit_rows(Eigen::Index begin, Eigen::Index count, Eigen::MatrixXd& responsibilities);
 		private:
-			DeviceData data_;
+			std::shared_ptr<DeviceData> data_;
 			mlb_em* em_ = nullptr;
 			unsigned int number_components_;
 		};
@@ -64,6 +77,8 @@ namespace ml
 		{
 		public:
 			KmDevice(Eigen::Ref<const Eigen::MatrixXd> data, unsigned int number_clusters);
+			/** On points that are already resident (shared with an EmDevice). */
+			KmDevice(std::shared_ptr<DeviceData> data, unsigned int number_clusters);
 			~KmDevice();
 			KmDevice(const KmDevice&) = delete;
 			KmDevice& operator=(const KmDevice&) = delete;
@@ -74,8 +89,11 @@ namespace ml
 			/** @return squared Frobenius norm of the centroid shift. */
 			double update();
 			void get_labels(std::vector<unsigned int>& labels);
+			/** Nearest centroid and squared distance for every column of `points` (D x m). */
+			void predict(Eigen::Ref<const Eigen::MatrixXd> points, std::vector<unsigned int>& labels, std::vector<double>& squared_distances);
+			const std::shared_ptr<DeviceData>& data() const { return data_; }
 		private:
-			DeviceData data_;
+			std::shared_ptr<DeviceData> data_;
 			mlb_km* km_ = nullptr;
 		};
 	}

@@ -8,6 +8,7 @@
 #include <iostream>
 #include <limits>
 #include <stdexcept>
+#include <typeinfo>
 
 #include "Backend.hpp"
 #include "ML/LinearAlgebra.hpp"
@@ -138,11 +139,28 @@ namespace ml
 
 		device_ = std::make_unique<detail::EmDevice>(data, number_components_);
 		if (maximise_first_) {
-			Eigen::MatrixXd initial(sample_size, number_components_);
-			responsibilities_initialiser_->init(data, prng_, number_components_, initial);
-			device_->maximise_from(initial);
+			const Clustering::ResponsibilitiesInitialiser& initialiser = *responsibilities_initialiser_;
+			if (typeid(initialiser) == typeid(Clustering::ClosestCentroid)) {
+				// Clustering.cpp:72-89 without the N x K host matrix: initial centroids as the initialiser draws them, the
+				// nearest-centroid pass by the K-means assignment kernel (same strict <, lowest index wins) on the points
+				// already in HBM, then the M-step of the one-hot responsibilities.
+				const auto& closest = static_cast<const Clustering::ClosestCentroid&>(initialiser);
+				Eigen::MatrixXd centroids(number_dimensions, number_components_);
+				initialise_centroids(*closest.centroids_initialiser(), data, centroids);
+				detail::KmDevice nearest(device_->data(), number_components_);
+				nearest.set_centroids(centroids);
+				std::int64_t changed = 0;
+				nearest.assign(changed);
+				std::vector<unsigned int> initial_labels;
+				nearest.get_labels(initial_labels);
+				device_->maximise_from_labels(initial_labels);
+			} else {
+				Eigen::MatrixXd initial(sample_size, number_components_);
+				responsibilities_initialiser_->init(data, prng_, number_components_, initial);
+				device_->maximise_from(initial);
+			}
 		} else {
-			means_initialiser_->init(data, prng_, number_components_, means_);
+			initialise_centroids(*means_initialiser_, data, means_);
 			const Eigen::MatrixXd sample_covariance(device_->sample_covariance());
 			for (unsigned int k = 0; k < number_components_; ++k) {
 				covariances_[k] = sample_covariance;
@@ -196,6 +214,16 @@ namespace ml
 			}
 		}
 		return converged_;
+	}
+
+	void EM::initialise_centroids(const Clustering::CentroidsInitialiser& initialiser, Eigen::Ref<const Eigen::MatrixXd> data, Eigen::Ref<Eigen::MatrixXd> centroids)
+	{
+		if (typeid(initialiser) == typeid(Clustering::KPP)) {
+			// the built-in K-means++: distance passes on the device, draws here (Clustering.cpp:39-59)
+			detail::kpp_on_device(*device_->data(), data, prng_, number_components_, centroids);
+		} else {
+			initialiser.init(data, prng_, number_components_, centroids);
+		}
 	}
 
 	void EM::fetch_parameters(Eigen::Index number_dimensions)
@@ -254,6 +282,19 @@ namespace ml
 			}
 			sqrt_covariance_determinants_[k] = sqrt_determinant;
 		}
+	}
+
+	Eigen::MatrixXd EM::assign_responsibilities(Eigen::Ref<const Eigen::MatrixXd> points) const
+	{
+		if (points.rows() != means().rows()) {
+			throw std::invalid_argument("Wrong number of rows");
+		}
+		if (!device_) {
+			throw std::logic_error("EM: no fitted device state");
+		}
+		Eigen::MatrixXd result;
+		device_->predict(points, result);
+		return result;
 	}
 
 	void EM::assign_responsibilities(Eigen::Ref<const Eigen::VectorXd> x, Eigen::Ref<Eigen::VectorXd> u) const

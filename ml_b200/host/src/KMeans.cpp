@@ -7,6 +7,7 @@
 #include <iostream>
 #include <limits>
 #include <stdexcept>
+#include <typeinfo>
 
 #include "Backend.hpp"
 
@@ -44,6 +45,7 @@ namespace ml
 			}
 			converged_ = false;
 			number_iterations_ = 0;
+			device_.reset();
 			centroids_.resize(number_dimensions, num_clusters_);
 			labels_.resize(sample_size);
 
@@ -58,7 +60,8 @@ namespace ml
 				return converged_;
 			}
 
-			detail::KmDevice device(data, num_clusters_);
+			device_ = std::make_unique<detail::KmDevice>(data, num_clusters_);
+			detail::KmDevice& device = *device_;
 			if (num_inits_ == 1) {
 				fit_once(data, device);
 			} else {
@@ -90,7 +93,13 @@ namespace ml
 		bool KMeans::fit_once(Eigen::Ref<const Eigen::MatrixXd> data, detail::KmDevice& device)
 		{
 			converged_ = false;
-			centroids_initialiser_->init(data, prng_, num_clusters_, centroids_);
+			const CentroidsInitialiser& initialiser = *centroids_initialiser_;
+			if (typeid(initialiser) == typeid(KPP)) {
+				// the built-in K-means++: distance passes on the device, draws here (Clustering.cpp:39-59)
+				detail::kpp_on_device(*device.data(), data, prng_, num_clusters_, centroids_);
+			} else {
+				initialiser.init(data, prng_, num_clusters_, centroids_);
+			}
 			device.set_centroids(centroids_);
 			for (unsigned int step = 0; step < maximum_steps_; ++step) {
 				std::int64_t changed = 0;
@@ -159,6 +168,19 @@ namespace ml
 				throw std::invalid_argument("KMeans: Null centroids initialiser");
 			}
 			centroids_initialiser_ = centroids_initialiser;
+		}
+
+		std::pair<std::vector<unsigned int>, std::vector<double>> KMeans::assign_labels(Eigen::Ref<const Eigen::MatrixXd> points) const
+		{
+			if (points.rows() != centroids_.rows()) {
+				throw std::invalid_argument("KMeans: wrong number of rows");
+			}
+			if (!device_) {
+				throw std::logic_error("KMeans: no fitted device state");
+			}
+			std::pair<std::vector<unsigned int>, std::vector<double>> result;
+			device_->predict(points, result.first, result.second);
+			return result;
 		}
 
 		std::pair<unsigned int, double> KMeans::assign_label(Eigen::Ref<const Eigen::VectorXd> x) const

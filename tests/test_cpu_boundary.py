@@ -76,6 +76,10 @@ def test_invalid_arguments_are_rejected_before_any_device_work():
     b, e = ctypes.c_int64(), ctypes.c_int64()
     assert lib.mlb_shard_range(100, 3, 0, ctypes.byref(b), ctypes.byref(e)) == cabi.MLB_EINVAL
     assert lib.mlb_em_step(None, None) == cabi.MLB_EINVAL
+    assert lib.mlb_data_kpp_update(None, None, 1, None) == cabi.MLB_EINVAL
+    assert lib.mlb_em_mstep_from_labels(None, None) == cabi.MLB_EINVAL
+    assert lib.mlb_em_predict(None, None, 0, 0, None, 0, None) == cabi.MLB_EINVAL
+    assert lib.mlb_km_predict(None, None, 0, 0, None, None) == cabi.MLB_EINVAL
 
 
 def test_host_layer_cpp_tests():
@@ -139,6 +143,18 @@ def test_cppyml_surface_and_errors():
     assert km.centroids.shape == (3, 2) and np.array_equal(km.centroids, x)
     assert km.labels == [0, 1, 2] and km.inertia == 0.0
     assert km.assign_label(x[1]) == (1, 0.0)
+    # the batched forms run on the device only: wrong shapes are ValueErrors, a model without device state fails loudly
+    assert callable(em.assign_responsibilities_batch) and callable(km.assign_labels)
+    with pytest.raises(ValueError):
+        em.assign_responsibilities_batch(np.zeros((4, 5)))
+    with pytest.raises(ValueError):
+        km.assign_labels(np.zeros((4, 5)))
+    with pytest.raises(RuntimeError):
+        em.assign_responsibilities_batch(np.zeros((4, 2)))   # N == K exact fit: nothing is resident
+    with pytest.raises(RuntimeError):
+        km.assign_labels(np.zeros((4, 2)))
+    with pytest.raises(TypeError):
+        km.assign_labels(np.zeros((4, 2), dtype=np.float32))
 
 
 def test_bench_reference_arm_runs_on_cpu():
