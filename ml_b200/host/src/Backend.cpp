@@ -2,7 +2,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <limits>
 #include <mutex>
+#include <numeric>
 #include <stdexcept>
 #include <string>
 
@@ -68,6 +70,24 @@ namespace ml
 			check(mlb_data_kpp_update(handle_, centroid, first ? 1 : 0, nearest.data()), "KPP distance pass");
 		}
 
+		Eigen::Index draw_discrete(const std::vector<double>& weights, std::default_random_engine& prng)
+		{
+			const size_t n = weights.size();
+			if (n < 2) {
+				return 0;   // the library keeps no probabilities then and draws nothing
+			}
+			const double sum = std::accumulate(weights.begin(), weights.end(), 0.0);
+			const double p = std::generate_canonical<double, std::numeric_limits<double>::digits>(prng);
+			double cumulative = 0;
+			for (size_t i = 0; i + 1 < n; ++i) {
+				cumulative += weights[i] / sum;
+				if (!(cumulative < p)) {
+					return static_cast<Eigen::Index>(i);
+				}
+			}
+			return static_cast<Eigen::Index>(n - 1);   // the last cumulative probability is set to one
+		}
+
 		void kpp_on_device(DeviceData& device_data, Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, const unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids)
 		{
 			const Eigen::Index dim = data.rows();
@@ -77,8 +97,7 @@ namespace ml
 				if (k > 0) {
 					device_data.kpp_update(newest.data(), k == 1, weights);
 				}
-				std::discrete_distribution<Eigen::Index> draw(weights.begin(), weights.end());
-				const Eigen::Index index = draw(prng);
+				const Eigen::Index index = draw_discrete(weights, prng);
 				std::copy_n(data.data() + index * data.outerStride(), dim, newest.begin());
 				std::copy_n(newest.begin(), dim, centroids.data() + static_cast<Eigen::Index>(k) * centroids.outerStride());
 			}

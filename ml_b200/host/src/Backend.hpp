@@ -42,6 +42,13 @@ namespace ml
 			Eigen::Index rows_ = 0, cols_ = 0;
 		};
 
+		/** What `std::discrete_distribution<Eigen::Index>(weights.begin(), weights.end())(prng)` returns and consumes
+		(Clustering.cpp:55-56), without the two N-sized temporaries the library builds per draw: the same sequential sum,
+		the same divisions, the same running partial sums, scanned until the first one not below the drawn number (which
+		is where the library's binary search over the monotone partial sums ends).  Pinned against the library on the CPU
+		(tests/cpp/host_tests.cpp). */
+		Eigen::Index draw_discrete(const std::vector<double>& weights, std::default_random_engine& prng);
+
 		/** KPP::init (ML/Clustering.cpp:39-59) with the distance passes on the device and the draws on the host:
 		the same std::discrete_distribution over the same weights, so the same centroids and PRNG stream. */
 		void kpp_on_device(DeviceData& device_data, Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids);

@@ -16,6 +16,7 @@
 #include "ML/EM.hpp"
 #include "ML/KMeans.hpp"
 #include "ML/LinearAlgebra.hpp"
+#include "src/Backend.hpp"
 
 extern "C" {
 void mlpp_oracle_centroids_init(int kind, const double* data, int64_t d, int64_t n, int64_t ld, unsigned k, unsigned seed, int set_seed, double* centroids);
@@ -65,6 +66,33 @@ static void test_initialisers()
         CHECK(resp(i, arg) == 1.0);
     }
     CHECK_THROWS(ml::Clustering::ClosestCentroid(nullptr), std::invalid_argument);
+}
+
+// detail::draw_discrete against the library call it stands for (Clustering.cpp:55-56): the same index and the same
+// generator state afterwards, for weight vectors shaped like KPP's (zeros at the chosen points, wide dynamic range).
+static void test_draw_discrete()
+{
+    std::mt19937_64 shapes(12345);
+    for (int trial = 0; trial < 400; ++trial) {
+        const size_t n = trial < 4 ? static_cast<size_t>(trial + 1) : 2 + shapes() % 5000;
+        std::vector<double> weights(n);
+        for (double& w : weights) {
+            const double u = static_cast<double>(shapes() >> 11) / 9007199254740992.0;
+            w = (shapes() % 7 == 0) ? 0.0 : std::exp(20.0 * u - 10.0);
+        }
+        if (trial % 5 == 0) std::fill(weights.begin(), weights.end(), 1.0);   // the first KPP draw
+        weights[shapes() % n] += 1e-3;   // never all zero
+        std::default_random_engine a, b;
+        a.seed(1000 + trial);
+        b.seed(1000 + trial);
+        for (int draw = 0; draw < 3; ++draw) {
+            std::discrete_distribution<Eigen::Index> library(weights.begin(), weights.end());
+            const Eigen::Index want = library(a);
+            const Eigen::Index got = ml::detail::draw_discrete(weights, b);
+            CHECK(got == want);
+            CHECK(a == b);
+        }
+    }
 }
 
 static void test_linear_algebra()
@@ -160,6 +188,7 @@ static void test_deterministic_fits()
 int main()
 {
     test_initialisers();
+    test_draw_discrete();
     test_linear_algebra();
     test_argument_errors();
     test_deterministic_fits();

@@ -83,11 +83,12 @@ def test_invalid_arguments_are_rejected_before_any_device_work():
 
 
 def test_host_layer_cpp_tests():
-    """tests/cpp/host_tests.cpp: initialiser PRNG streams bit-equal to the oracle, LinearAlgebra identities,
+    """tests/cpp/host_tests.cpp: initialiser PRNG streams bit-equal to the oracle, the streamed discrete draw of the
+    device-assisted KPP bit-equal to std::discrete_distribution, LinearAlgebra identities,
     argument errors, N == K exact fits (Tests/test_EM.cpp:126-144, Tests/test_KMeans.cpp:108-127)."""
     exe = os.path.join(ROOT, "build", "host_tests")
     lib_dir, oracle_dir = os.path.join(ROOT, "ml_b200", "lib"), os.path.join(ROOT, "oracle")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "ml_b200", "host"),
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "ml_b200", "host"), "-I", os.path.join(ROOT, "include"),
                            "-isystem", os.path.join(ROOT, "ml_b200", "host", "eigen_compat"), os.path.join(ROOT, "tests", "cpp", "host_tests.cpp"),
                            "-o", exe, "-L", lib_dir, "-lML", "-lmlb200", "-L", oracle_dir, "-lmlpp_oracle",
                            f"-Wl,-rpath,{lib_dir}", f"-Wl,-rpath,{oracle_dir}"])

@@ -77,6 +77,37 @@ def test_kmeans_is_bitwise_invariant_in_the_gpu_count():
             assert np.array_equal(a, b), g
 
 
+def _seeding_run(n_devices, data, k, labels):
+    """KPP distance passes, the M-step from labels and prediction on a G-GPU context."""
+    from ml_b200 import cabi
+    ctx = cabi.Context(n_devices)
+    d_data = cabi.Data.upload(ctx, data)
+    nearest = [d_data.kpp_update(data[i * 7], first=(i == 0)).copy() for i in range(3)]
+    em = cabi.Em(d_data, k)
+    em.mstep_from_labels(labels)
+    params = em.get_params()
+    resp, pred = em.predict(data[:3000])
+    km = cabi.Km(d_data, k)
+    km.set_centroids(np.ascontiguousarray(data[:k].T))
+    km_labels, km_dist = km.predict(data[:3000])
+    km.close(); em.close(); d_data.close(); ctx.close()
+    return (*nearest, *params, resp, pred, km_labels, km_dist)
+
+
+def test_seeding_and_prediction_are_bitwise_invariant_in_the_gpu_count():
+    have = _device_count()
+    if have < 2:
+        pytest.skip("needs at least 2 GPUs")
+    data, labels, _ = synthetic_gmm(30011, 8, 16, seed=63)
+    ref = _seeding_run(1, data, 16, labels)
+    for g in (2, 4, 8):
+        if g > have:
+            break
+        got = _seeding_run(g, data, 16, labels)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b), g
+
+
 def test_bench_under_torchrun_two_ranks():
     """bench.py launched the way the driver launches it for N = 2: one rank per GPU, one JSON line from rank 0."""
     if _device_count() < 2:

@@ -66,7 +66,7 @@ def em_predict_case(ctx, n_fit, m, d, k):
     em = cabi.Em(data, k)
     em.set_params(data.download(0, k).T, np.repeat(em.sample_covariance()[None], k, axis=0), np.full(k, 1.0 / k))
     em.run_steps(3)
-    queries = data.download(0, m)
+    queries = np.ascontiguousarray(np.tile(data.download(0, n_fit), (m // n_fit, 1)))
     em.predict(queries[:1000])
     t0 = time.perf_counter()
     _, labels = em.predict(queries, want_responsibilities=False)
@@ -85,7 +85,7 @@ def km_predict_case(ctx, n_fit, m, d, k):
     km = cabi.Km(data, k)
     km.set_centroids(data.download(0, k).T)
     km.assign(); km.update()
-    queries = data.download(0, m)
+    queries = np.ascontiguousarray(np.tile(data.download(0, n_fit), (m // n_fit, 1)))
     km.predict(queries[:1000])
     t0 = time.perf_counter()
     labels, dist = km.predict(queries)
