@@ -165,6 +165,31 @@ def cpu_baseline(n_cpu, d, k, steps, warmup, kind="em"):
             "pinned_by": "oracle/_ref (reference sources + Eigen stand-in): bit-identical, tests/test_oracle_vs_reference.py" if oracle.ref_available() else "reference property tests only"}
 
 
+def reference_build_timing(n_ref, d, k, kind, steps=3):
+    """For the record next to the port's number: the reference's OWN translation units (oracle/_ref: ML/EM.cpp,
+    ML/KMeans.cpp, ... compiled against the first-party Eigen stand-in) on a smaller sample of the same mixture.  Whole
+    fit / iterations (the reference has no per-step clock).  None when oracle/_ref was not built (no /root/reference)."""
+    import time
+    import numpy as np
+    import oracle
+    from tests.datasets import synthetic_gmm
+    if not oracle.ref_available():
+        return None
+    data, _, _ = synthetic_gmm(n_ref, d, min(k, 64), seed=DATA_SEED % 1000, spread=10.0)
+    init = np.ascontiguousarray(data[:k].T)
+    t0 = time.perf_counter()
+    if kind == "em":
+        fit = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=steps, absolute_tolerance=0.0,
+                            relative_tolerance=0.0, want_responsibilities=False, impl="reference")
+    else:
+        fit = oracle.kmeans_fit(data, k, init=oracle.EXPLICIT, explicit_means=init, maximum_steps=steps, absolute_tolerance=0.0, impl="reference")
+    seconds = time.perf_counter() - t0
+    iterations = max(1, fit.iterations)
+    return {"value": n_ref * k * iterations / seconds / 1e9, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"oracle/_ref (the reference's own sources + Eigen stand-in), N={n_ref} D={d} K={k}, whole fit of {iterations} iterations including initialisation",
+            "note": "the stand-in evaluates Eigen expressions eagerly into heap temporaries, so this is slower than a real-Eigen build; the port above is the baseline"}
+
+
 CPU_SAMPLE = {"c2": (200_000, 500_000), "c3": (20_000, 50_000), "c4": (4_000, 6_000), "c5": (20_000, 40_000)}   # (--impl reference, cpu_baseline)
 
 
@@ -183,6 +208,7 @@ def run_reference(args):
     kind, n_gpu, d, k = WORKLOADS[args.workload]
     n_cpu = args.cpu_sample or CPU_SAMPLE[args.workload][0]
     base = cpu_baseline(n_cpu, d, k, args.steps, args.warmup, kind)
+    ref_build = reference_build_timing(max(1000, n_cpu // 10), d, k, kind)
     line = {
         "impl": "reference", "metric": METRIC if kind == "em" else METRIC_KM, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -193,6 +219,8 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if ref_build:
+        line["reference_build"] = ref_build
     print(json.dumps(line), flush=True)
 
 
