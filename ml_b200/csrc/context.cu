@@ -145,6 +145,12 @@ Layout Layout::make(int64_t n_total)
     int64_t c = n_total / (8 * kSmCount * 6);
     c = (c + 127) / 128 * 128;
     c = std::max<int64_t>(128, std::min<int64_t>(2048, c));
+    // MLB200_CHUNK: developer override (a multiple of 128), used to reproduce on one GPU the chunking a larger job
+    // has (the chunk size follows the TOTAL point count).  Every rank of a job must see the same value.
+    if (const char* env = std::getenv("MLB200_CHUNK")) {
+        const long v = std::atol(env);
+        if (v >= 128 && v <= 4096 && v % 128 == 0) c = v;
+    }
     lay.chunk = static_cast<int>(c);
     lay.n_chunks = (n_total + c - 1) / c;
     for (int v = 0; v <= kVirtualShards; ++v) lay.vshard_chunk[v] = lay.n_chunks * v / kVirtualShards;

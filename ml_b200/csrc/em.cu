@@ -806,6 +806,52 @@ static int enqueue_step(mlb_em* em)
     return MLB_OK;
 }
 
+// maximisation_step from responsibilities already on the devices: dev[g] is column-major, local rows of GPU g, leading
+// dimension max(1, n_local).  Frees the buffers.
+static int mstep_from_device(mlb_em* em, std::vector<double*>& dev, int rc)
+{
+    mlb_ctx* ctx = em->ctx;
+    if (rc == MLB_OK) {
+        rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+            const int64_t n = em->data->shards[g].n();
+            if (em->path == 2) {
+                if (n == 0) return MLB_OK;
+                const long long total = static_cast<long long>(n) * em->KP;
+                em_split_import_r_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->gpus[g].stream>>>(dev[g], n, n, em->k, em->KP, em->gpus[g].r);
+                MLB_CUDA(cudaGetLastError());
+                ++em->launches;
+                return launch_split(em, g, em->gpus[g].theta[em->cur], false, false);
+            }
+            EmArgs a = base_args(em, g);
+            a.r_in = dev[g];
+            a.r_ld = std::max<int64_t>(1, n);  // device copy: local rows only
+            return launch_em(em, em->fn_mstep, a, g, em->gpus[g].grid);
+        });
+        if (rc == MLB_OK) {
+            std::vector<double*> partials, vsum;
+            for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
+            rc = reduce_and_exchange(em->data, partials, vsum, em->SV);
+            em->launches += static_cast<int64_t>(ctx->gpus.size());
+        }
+        if (rc == MLB_OK)
+            rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, true, em->cur, false); });
+        if (rc == MLB_OK) rc = mlb_ctx_synchronize(ctx);
+    }
+    for (size_t g = 0; g < dev.size(); ++g)
+        if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(dev[g], ctx->gpus[g].stream); }
+    if (rc == MLB_OK) { em->have_params = true; em->have_step = false; }
+    return rc;
+}
+
+// One-hot responsibilities (Clustering.cpp:76,87) from labels: r[i + k * ld] = (labels[i] == k).
+__global__ void em_onehot_kernel(const unsigned* __restrict__ labels, long long n, int k, double* __restrict__ r)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned label = labels[i];
+    for (int kk = 0; kk < k; ++kk) r[i + static_cast<long long>(kk) * n] = label == static_cast<unsigned>(kk) ? 1.0 : 0.0;
+}
+
 }  // namespace mlb
 
 extern "C" {
@@ -1099,52 +1145,6 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
         for (int b = 0; b < d; ++b)
             cov_out[a + static_cast<size_t>(b) * d] = (m2[a + static_cast<size_t>(b) * d] - m1[a] * m1[b] / count) / (count - 1.0);
     return MLB_OK;
-}
-
-// maximisation_step from responsibilities already on the devices: dev[g] is column-major, local rows of GPU g, leading
-// dimension max(1, n_local).  Frees the buffers.
-static int mstep_from_device(mlb_em* em, std::vector<double*>& dev, int rc)
-{
-    mlb_ctx* ctx = em->ctx;
-    if (rc == MLB_OK) {
-        rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int {
-            const int64_t n = em->data->shards[g].n();
-            if (em->path == 2) {
-                if (n == 0) return MLB_OK;
-                const long long total = static_cast<long long>(n) * em->KP;
-                em_split_import_r_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->gpus[g].stream>>>(dev[g], n, n, em->k, em->KP, em->gpus[g].r);
-                MLB_CUDA(cudaGetLastError());
-                ++em->launches;
-                return launch_split(em, g, em->gpus[g].theta[em->cur], false, false);
-            }
-            EmArgs a = base_args(em, g);
-            a.r_in = dev[g];
-            a.r_ld = std::max<int64_t>(1, n);  // device copy: local rows only
-            return launch_em(em, em->fn_mstep, a, g, em->gpus[g].grid);
-        });
-        if (rc == MLB_OK) {
-            std::vector<double*> partials, vsum;
-            for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
-            rc = reduce_and_exchange(em->data, partials, vsum, em->SV);
-            em->launches += static_cast<int64_t>(ctx->gpus.size());
-        }
-        if (rc == MLB_OK)
-            rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, true, em->cur, false); });
-        if (rc == MLB_OK) rc = mlb_ctx_synchronize(ctx);
-    }
-    for (size_t g = 0; g < dev.size(); ++g)
-        if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(dev[g], ctx->gpus[g].stream); }
-    if (rc == MLB_OK) { em->have_params = true; em->have_step = false; }
-    return rc;
-}
-
-// One-hot responsibilities (Clustering.cpp:76,87) from labels: r[i + k * ld] = (labels[i] == k).
-__global__ void em_onehot_kernel(const unsigned* __restrict__ labels, long long n, int k, double* __restrict__ r)
-{
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned label = labels[i];
-    for (int kk = 0; kk < k; ++kk) r[i + static_cast<long long>(kk) * n] = label == static_cast<unsigned>(kk) ? 1.0 : 0.0;
 }
 
 int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t ld)
