@@ -17,6 +17,12 @@ constexpr int kSmallSub = 16;   // points per warp sub-tile
 #ifndef MLB_EM_SMALL_MINB
 #define MLB_EM_SMALL_MINB 4
 #endif
+// At most 6 accumulator tiles (K <= 8, or D <= 4 with K <= 16): 96 registers suffice without spilling and a fifth
+// resident CTA per SM is worth 4-6 % (measured per 10M points: D = 8, K = 8: 0.832 -> 0.787 ms; D = 4, K = 8:
+// 0.464 -> 0.441 ms).  With 12 tiles (C2: D = 8, K = 16) the same bound spills and costs 11 % (1.337 -> 1.488 ms).
+#ifndef MLB_EM_SMALL_MINB_K8
+#define MLB_EM_SMALL_MINB_K8 5
+#endif
 
 // Slot of the constant-1 feature (weighted count): the first dead E-step slot if the packing has one (DQ odd), else a
 // new slot after the last E-step slot.
@@ -29,7 +35,7 @@ constexpr size_t em_small_smem_bytes(int DP, int KP)
 }
 
 template <int DP, int KP, int MODE>
-__global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) * (KP / 8) <= 12) ? MLB_EM_SMALL_MINB : 3)) em_small_kernel(const EmArgs p)
+__global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) * (KP / 8) <= 6) ? MLB_EM_SMALL_MINB_K8 : (em_small_nm(DP) * (KP / 8) <= 12) ? MLB_EM_SMALL_MINB : 3)) em_small_kernel(const EmArgs p)
 {
     constexpr int NT = KP / 8, DQ = DP / 4, NE = em_ne(DP), NM = em_small_nm(DP);
     constexpr int RS = KP + 4, PS = NM * 8 + 4;

@@ -97,13 +97,17 @@ def km_predict_case(ctx, n_fit, m, d, k):
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])   # e.g. `kpp_init`; default: everything
+    want = lambda kind: not only or kind in only
     ctx = cabi.Context(1)
-    out = []
-    for n, d in [(12_500_000, 16), (12_500_000, 32), (10_000_000, 8), (2_500_000, 64)]:
-        out.append(kpp_pass_case(ctx, n, d))
-        print(json.dumps(out[-1]), flush=True)
-    out.append(em_predict_case(ctx, 1_000_000, 4_000_000, 16, 32)); print(json.dumps(out[-1]), flush=True)
-    out.append(em_predict_case(ctx, 1_000_000, 4_000_000, 8, 16)); print(json.dumps(out[-1]), flush=True)
-    out.append(km_predict_case(ctx, 1_000_000, 4_000_000, 32, 256)); print(json.dumps(out[-1]), flush=True)
+    if want("kpp_pass"):
+        for n, d in [(12_500_000, 16), (12_500_000, 32), (10_000_000, 8), (2_500_000, 64)]:
+            print(json.dumps(kpp_pass_case(ctx, n, d)), flush=True)
+    if want("em_predict"):
+        print(json.dumps(em_predict_case(ctx, 1_000_000, 4_000_000, 16, 32)), flush=True)
+        print(json.dumps(em_predict_case(ctx, 1_000_000, 4_000_000, 8, 16)), flush=True)
+    if want("km_predict"):
+        print(json.dumps(km_predict_case(ctx, 1_000_000, 4_000_000, 32, 256)), flush=True)
     ctx.close()
-    out.append(kpp_init_case(2_000_000, 16, 32)); print(json.dumps(out[-1]), flush=True)
+    if want("kpp_init"):
+        print(json.dumps(kpp_init_case(2_000_000, 16, 32)), flush=True)
