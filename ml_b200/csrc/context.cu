@@ -8,7 +8,10 @@
 #include <cstring>
 #include <mutex>
 #include <random>
+#include <string>
+#include <thread>
 #include <type_traits>
+#include <vector>
 
 #include "internal.h"
 
@@ -60,36 +63,143 @@ const NcclApi* nccl()
     return &api;
 }
 
-constexpr size_t kBounceBytes = 8u << 20;
+constexpr size_t kBounceBytes = 4u << 20;
+constexpr size_t kThreadedCopyBytes = 16u << 20;   // below this one thread does the whole copy
 
-int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes)
+static int ensure_bounce(Gpu& gpu)
 {
-    if (bytes == 0) return MLB_OK;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 2 * kCopyThreadsMax; ++i) {
         if (!gpu.bounce[i]) {
             MLB_CUDA(cudaMallocHost(&gpu.bounce[i], kBounceBytes));
             MLB_CUDA(cudaEventCreateWithFlags(&gpu.bounce_ev[i], cudaEventDisableTiming));
         }
     }
+    return MLB_OK;
+}
+
+static bool is_pinned_host(const void* ptr)
+{
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();   // older drivers report unregistered host memory as an error
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+static int copy_threads(size_t bytes)
+{
+    if (bytes < kThreadedCopyBytes) return 1;
+    static const int configured = [] {
+        int t = static_cast<int>(std::min<unsigned>(kCopyThreadsMax, std::max(1u, std::thread::hardware_concurrency() / 2)));
+        if (const char* env = std::getenv("MLB200_COPY_THREADS")) t = std::max(1, std::min(kCopyThreadsMax, std::atoi(env)));
+        return t;
+    }();
+    return configured;
+}
+
+// Runs body(t) on `threads` host threads (the caller is thread 0) and returns the first failure.
+template <class F>
+static int run_copy_threads(int threads, F&& body)
+{
+    std::vector<int> rc(static_cast<size_t>(threads), MLB_OK);
+    std::vector<std::string> why(static_cast<size_t>(threads));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t)
+        pool.emplace_back([&, t] {
+            rc[t] = body(t);
+            if (rc[t] != MLB_OK) why[t] = mlb_last_error();   // the error text is thread-local
+        });
+    rc[0] = body(0);
+    for (std::thread& th : pool) th.join();
+    for (int t = 0; t < threads; ++t)
+        if (rc[t] != MLB_OK) {
+            if (t > 0) set_error("%s", why[t].c_str());
+            return rc[t];
+        }
+    return MLB_OK;
+}
+
+int staged_h2d(Gpu& gpu, void* dst_device, const void* src, size_t rows, size_t row_bytes, size_t src_stride)
+{
+    const size_t total = rows * row_bytes;
+    if (total == 0) return MLB_OK;
+    const bool contiguous = src_stride == row_bytes || rows == 1;
+    if (total < (1u << 20) || is_pinned_host(src)) {
+        if (contiguous) MLB_CUDA(cudaMemcpyAsync(dst_device, src, total, cudaMemcpyHostToDevice, gpu.stream));
+        else MLB_CUDA(cudaMemcpy2DAsync(dst_device, row_bytes, src, src_stride, row_bytes, rows, cudaMemcpyHostToDevice, gpu.stream));
+        return MLB_OK;
+    }
+    MLB_TRY(ensure_bounce(gpu));
+    const size_t pieces = (total + kBounceBytes - 1) / kBounceBytes;
+    const int threads = static_cast<int>(std::min<size_t>(copy_threads(total), pieces));
+    const char* in = static_cast<const char*>(src);
+    char* out = static_cast<char*>(dst_device);
+    return run_copy_threads(threads, [&](int t) -> int {
+        MLB_CUDA(cudaSetDevice(gpu.device));
+        int turn = 0;
+        for (size_t piece = static_cast<size_t>(t); piece < pieces; piece += static_cast<size_t>(threads), ++turn) {
+            const int slot = 2 * t + (turn & 1);
+            const size_t off = piece * kBounceBytes, len = std::min(kBounceBytes, total - off);
+            MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[slot]));   // the last DMA out of this buffer (this call or an earlier one)
+            char* stage = static_cast<char*>(gpu.bounce[slot]);
+            if (contiguous) {
+                std::memcpy(stage, in + off, len);
+            } else {
+                // logical bytes [off, off + len) of the dense image, gathered from the strided rows
+                size_t row = off / row_bytes, col = off - row * row_bytes, done = 0;
+                while (done < len) {
+                    const size_t take = std::min(row_bytes - col, len - done);
+                    std::memcpy(stage + done, in + row * src_stride + col, take);
+                    done += take;
+                    ++row;
+                    col = 0;
+                }
+            }
+            MLB_CUDA(cudaMemcpyAsync(out + off, stage, len, cudaMemcpyHostToDevice, gpu.stream));
+            MLB_CUDA(cudaEventRecord(gpu.bounce_ev[slot], gpu.stream));
+        }
+        return MLB_OK;
+    });
+}
+
+int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes)
+{
+    if (bytes == 0) return MLB_OK;
+    if (is_pinned_host(dst)) {
+        MLB_CUDA(cudaMemcpyAsync(dst, src_device, bytes, cudaMemcpyDeviceToHost, gpu.stream));
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    }
+    MLB_TRY(ensure_bounce(gpu));
+    const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
+    const int threads = static_cast<int>(std::min<size_t>(copy_threads(bytes), pieces));
     char* out = static_cast<char*>(dst);
     const char* in = static_cast<const char*>(src_device);
-    size_t prev_off = 0, prev_len = 0;
-    int i = 0;
-    for (size_t off = 0; off < bytes; off += kBounceBytes, ++i) {
-        const size_t len = std::min(kBounceBytes, bytes - off);
-        const int slot = i & 1;
-        MLB_CUDA(cudaMemcpyAsync(gpu.bounce[slot], in + off, len, cudaMemcpyDeviceToHost, gpu.stream));
-        MLB_CUDA(cudaEventRecord(gpu.bounce_ev[slot], gpu.stream));
-        if (i > 0) {
-            MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[slot ^ 1]));
-            std::memcpy(out + prev_off, gpu.bounce[slot ^ 1], prev_len);
+    return run_copy_threads(threads, [&](int t) -> int {
+        MLB_CUDA(cudaSetDevice(gpu.device));
+        // two buffers per thread: the DMA of this thread's next piece runs while it copies the previous one out
+        size_t prev_off = 0, prev_len = 0;
+        int turn = 0;
+        for (size_t piece = static_cast<size_t>(t); piece < pieces; piece += static_cast<size_t>(threads), ++turn) {
+            const int slot = 2 * t + (turn & 1);
+            const size_t off = piece * kBounceBytes, len = std::min(kBounceBytes, bytes - off);
+            MLB_CUDA(cudaMemcpyAsync(gpu.bounce[slot], in + off, len, cudaMemcpyDeviceToHost, gpu.stream));
+            MLB_CUDA(cudaEventRecord(gpu.bounce_ev[slot], gpu.stream));
+            if (turn > 0) {
+                MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[slot ^ 1]));
+                std::memcpy(out + prev_off, gpu.bounce[slot ^ 1], prev_len);
+            }
+            prev_off = off;
+            prev_len = len;
         }
-        prev_off = off;
-        prev_len = len;
-    }
-    MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[(i - 1) & 1]));
-    std::memcpy(out + prev_off, gpu.bounce[(i - 1) & 1], prev_len);
-    return MLB_OK;
+        if (turn > 0) {
+            const int last = 2 * t + ((turn - 1) & 1);
+            MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[last]));
+            std::memcpy(out + prev_off, gpu.bounce[last], prev_len);
+        }
+        return MLB_OK;
+    });
 }
 
 int KernelTimer::begin(cudaStream_t stream)
@@ -543,7 +653,7 @@ int mlb_ctx_destroy(mlb_ctx* ctx)
         if (gpu.comm && nccl()) nccl()->CommDestroy(gpu.comm);
         if (gpu.ev0) cudaEventDestroy(gpu.ev0);
         if (gpu.ev1) cudaEventDestroy(gpu.ev1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 2 * kCopyThreadsMax; ++i) {
             if (gpu.bounce[i]) cudaFreeHost(gpu.bounce[i]);
             if (gpu.bounce_ev[i]) cudaEventDestroy(gpu.bounce_ev[i]);
         }
@@ -669,12 +779,7 @@ int mlb_data_upload(mlb_ctx* ctx, const double* x, int64_t n, int64_t n_total, i
         MLB_CUDA(cudaMallocAsync(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d, gpu.stream));
         if (sh.n() > 0) {
             const double* src = x + (sh.begin - host_begin) * ld;
-            if (ld == d) {
-                MLB_CUDA(cudaMemcpyAsync(sh.x, src, sizeof(double) * sh.n() * d, cudaMemcpyHostToDevice, gpu.stream));
-            } else {
-                MLB_CUDA(cudaMemcpy2DAsync(sh.x, sizeof(double) * d, src, sizeof(double) * ld, sizeof(double) * d, sh.n(),
-                                           cudaMemcpyHostToDevice, gpu.stream));
-            }
+            MLB_TRY(staged_h2d(gpu, sh.x, src, static_cast<size_t>(sh.n()), sizeof(double) * d, sizeof(double) * ld));
         }
         return MLB_OK;
     });

@@ -1158,8 +1158,7 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
         const int64_t n = std::max<int64_t>(1, sh.n());
         MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
         if (sh.n() > 0)
-            MLB_CUDA(cudaMemcpy2DAsync(dev[g], sizeof(double) * n, resp + (sh.begin - host_begin), sizeof(double) * ld, sizeof(double) * sh.n(),
-                                       em->k, cudaMemcpyHostToDevice, gpu.stream));
+            MLB_TRY(staged_h2d(gpu, dev[g], resp + (sh.begin - host_begin), static_cast<size_t>(em->k), sizeof(double) * sh.n(), sizeof(double) * ld));
         return MLB_OK;
     });
     return mstep_from_device(em, dev, rc);
@@ -1185,7 +1184,7 @@ int mlb_em_mstep_from_labels(mlb_em* em, const unsigned int* labels)
         MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&dev_labels[g], sizeof(unsigned) * n, gpu.stream));
         if (sh.n() > 0) {
-            MLB_CUDA(cudaMemcpyAsync(dev_labels[g], labels + (sh.begin - host_begin), sizeof(unsigned) * sh.n(), cudaMemcpyHostToDevice, gpu.stream));
+            MLB_TRY(staged_h2d(gpu, dev_labels[g], labels + (sh.begin - host_begin), 1, sizeof(unsigned) * sh.n(), sizeof(unsigned) * sh.n()));
             em_onehot_kernel<<<static_cast<unsigned>((sh.n() + 255) / 256), 256, 0, gpu.stream>>>(dev_labels[g], sh.n(), em->k, dev[g]);
             MLB_CUDA(cudaGetLastError());
             ++em->launches;
@@ -1293,8 +1292,7 @@ int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double*
         for (int64_t off = 0; off < m; off += kStagePoints) {
             const int64_t n = std::min<int64_t>(kStagePoints, m - off);
             const double* src = x + off * ld_x;
-            if (ld_x == d) MLB_CUDA(cudaMemcpyAsync(xd, src, sizeof(double) * n * d, cudaMemcpyHostToDevice, gpu.stream));
-            else MLB_CUDA(cudaMemcpy2DAsync(xd, sizeof(double) * d, src, sizeof(double) * ld_x, sizeof(double) * d, n, cudaMemcpyHostToDevice, gpu.stream));
+            MLB_TRY(staged_h2d(gpu, xd, src, static_cast<size_t>(n), sizeof(double) * d, sizeof(double) * ld_x));
             if (em->path == 2) {
                 // E kernel on the staged points (responsibilities into r_tmp), then the transposing emit kernel
                 EmSplitArgs a = split_args(em, 0, eg.theta[em->cur]);

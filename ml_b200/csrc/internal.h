@@ -70,6 +70,7 @@ const NcclApi* nccl();
     } while (0)
 
 constexpr int kVirtualShards = MLB_VIRTUAL_SHARDS;
+constexpr int kCopyThreadsMax = 4;   // host threads that pack / unpack the pinned bounce buffers of one large copy
 constexpr int kSmCount = 148;  // B200
 
 // e / d for 0 <= e < 65536 and 1 <= d <= 128 without the ~30-instruction integer division the compiler emits for a
@@ -100,9 +101,9 @@ struct Gpu {
     cudaStream_t stream = nullptr;
     ncclComm_t comm = nullptr;  // null when world == 1
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    // pinned bounce buffers for device -> pageable-host copies (staged_d2h)
-    void* bounce[2] = {nullptr, nullptr};
-    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    // pinned bounce buffers for copies from / to pageable host memory (staged_h2d, staged_d2h): two per copy thread
+    void* bounce[2 * kCopyThreadsMax] = {};
+    cudaEvent_t bounce_ev[2 * kCopyThreadsMax] = {};
 };
 
 }  // namespace mlb
@@ -161,9 +162,18 @@ int for_each_gpu(mlb_ctx* ctx, F&& body)
 // Fixed summation order => deterministic and independent of the GPU count.
 int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s);
 
-// Device -> host copy into memory that is probably pageable (a numpy array, a std::vector): chunks go through two
-// pinned bounce buffers, the DMA of chunk i overlapping the CPU copy-out of chunk i - 1.  A direct cudaMemcpy into
-// pageable memory runs at ~4 GB/s on these boxes; this path is bounded by the CPU copy (~10+ GB/s).  Synchronous.
+// Copies between host memory that is probably pageable (a numpy array, a std::vector, an Eigen matrix) and the device.
+// A direct cudaMemcpy of pageable memory runs at ~10 GB/s host -> device and ~4 GB/s device -> host on these boxes (one
+// driver thread staging through its own pinned buffer; first-touch page faults on fresh destination pages).  Large
+// copies are therefore cut into 4 MB pieces that up to four host threads pack into / unpack from pinned bounce buffers
+// (two per thread: the DMA of one piece overlaps the CPU copy of the next), so the DMA engine, not a single memcpy, is
+// the bound.  Pinned host memory (cudaMallocHost / cudaHostRegister) and small copies go straight to cudaMemcpyAsync.
+//
+// staged_h2d: the source is `rows` rows of `row_bytes` bytes, `src_stride` bytes apart (src_stride == row_bytes: one
+// contiguous block); the destination is dense.  On return the source has been read completely (the caller may free
+// it); the DMAs are ordered on gpu.stream like any other work.
+int staged_h2d(Gpu& gpu, void* dst_device, const void* src, size_t rows, size_t row_bytes, size_t src_stride);
+// staged_d2h: synchronous; on return dst holds the data.
 int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes);
 
 // Event pairs around the launches of one kernel on one stream (roofline timing for bench.py).

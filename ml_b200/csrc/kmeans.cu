@@ -891,8 +891,7 @@ int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigne
         for (int64_t off = 0; off < m; off += kStage) {
             const int64_t n = std::min<int64_t>(kStage, m - off);
             const double* src = x + off * ld_x;
-            if (ld_x == d) MLB_CUDA(cudaMemcpyAsync(xd, src, sizeof(double) * n * d, cudaMemcpyHostToDevice, gpu.stream));
-            else MLB_CUDA(cudaMemcpy2DAsync(xd, sizeof(double) * d, src, sizeof(double) * ld_x, sizeof(double) * d, n, cudaMemcpyHostToDevice, gpu.stream));
+            MLB_TRY(staged_h2d(gpu, xd, src, static_cast<size_t>(n), sizeof(double) * d, sizeof(double) * ld_x));
             KmArgs a{};
             a.x = xd; a.n_local = n; a.d = d; a.k = km->k; a.KP = km->KP;
             a.shift = km->data->shards[0].shift; a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
