@@ -165,6 +165,43 @@ def cpu_baseline(n_cpu, d, k, steps, warmup, kind="em"):
             "pinned_by": "oracle/_ref (reference sources + Eigen stand-in): bit-identical, tests/test_oracle_vs_reference.py" if oracle.ref_available() else "reference property tests only"}
 
 
+_ALL_CORES_SNIPPET = """
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+import oracle
+from tests.datasets import synthetic_gmm
+n, d, k, steps, warmup, kind, seed = {n}, {d}, {k}, {steps}, {warmup}, {kind!r}, {seed}
+data, _, _ = synthetic_gmm(n, d, min(k, 64), seed=seed, spread=10.0)
+init = np.ascontiguousarray(data[:k].T)
+if kind == "em":
+    fit = oracle.em_fit(data, k, means_init=oracle.EXPLICIT, explicit_means=init, maximum_steps=warmup + steps, absolute_tolerance=0.0,
+                        relative_tolerance=0.0, want_responsibilities=False)
+else:
+    fit = oracle.kmeans_fit(data, k, init=oracle.EXPLICIT, explicit_means=init, maximum_steps=warmup + steps, absolute_tolerance=0.0)
+print(float(np.mean(fit.step_seconds[warmup:])))
+"""
+
+
+def cpu_all_cores(n_cpu, d, k, steps, warmup, kind):
+    """SURVEY.md 8(d), optional figure: the reference algorithm has no threads, so "all host cores" means one
+    independent single-threaded fit per core, each on its own sample of n_cpu points (what a user could do by hand with
+    N-fold sharded data and no statistics exchange).  Aggregate throughput = cores * n_cpu * K / slowest mean step."""
+    import subprocess
+    cores = os.cpu_count() or 1
+    procs = [subprocess.Popen([sys.executable, "-c", _ALL_CORES_SNIPPET.format(root=ROOT, n=n_cpu, d=d, k=k, steps=steps, warmup=warmup, kind=kind,
+                                                                                seed=(DATA_SEED + 1 + i) % 1000)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"))
+             for i in range(cores)]
+    means = []
+    for p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            return None
+        means.append(float(out.strip().splitlines()[-1]))
+    return {"value": cores * n_cpu * k / max(means) / 1e9, "unit": UNIT, "cores": cores,
+            "sample": f"{cores} independent single-threaded oracle fits, N={n_cpu} points each, {steps} timed iterations after {warmup} warm-up"}
+
+
 def reference_build_timing(n_ref, d, k, kind, steps=3):
     """For the record next to the port's number: the reference's OWN translation units (oracle/_ref: ML/EM.cpp,
     ML/KMeans.cpp, ... compiled against the first-party Eigen stand-in) on a smaller sample of the same mixture.  Whole
@@ -442,6 +479,9 @@ def main():
         if world == 1 and not args.no_cpu:
             n_cpu = args.cpu_sample or CPU_SAMPLE[args.workload][1]
             line["cpu_baseline"] = cpu_baseline(n_cpu, d, k, 3, 1, kind)
+            all_cores = cpu_all_cores(max(1000, n_cpu // 4), d, k, 3, 1, kind)
+            if all_cores:
+                line["cpu_baseline"]["all_cores"] = all_cores
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
