@@ -277,9 +277,9 @@ class EmRunner:
     def step_sync(self):
         return self.obj.step()          # reads the log-likelihood back, as EM::fit's convergence test needs
 
-    def results(self):
+    def results(self, labels_out=None):
         params = self.obj.get_params()
-        _, labels = self.obj.emit(want_responsibilities=False, want_labels=True)
+        _, labels = self.obj.emit(want_responsibilities=False, want_labels=True, labels_out=labels_out)
         return params, labels
 
     def result_bytes(self, n_local, d):
@@ -312,8 +312,8 @@ class KmRunner:
         self.obj.update()
         return inertia
 
-    def results(self):
-        return self.obj.get_centroids(), self.obj.get_labels()
+    def results(self, labels_out=None):
+        return self.obj.get_centroids(), self.obj.get_labels(labels_out)
 
     def result_bytes(self, n_local, d):
         return n_local * 4 + d * self.k * 8
@@ -407,6 +407,7 @@ def main():
         begin, _ = cabi.shard_range(n_total, world, rank)
         host_np = host.numpy()
         host_np[:] = data.download(begin, n_local)
+        labels_pinned = torch.empty(n_local, dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)   # the result buffer, pinned like the input
         run.obj.close(); data.close()
         run = data = None
 
@@ -418,7 +419,7 @@ def main():
             last = 0.0
             for _ in range(args.steps):
                 last = r2.step_sync()
-            params, labels = r2.results()
+            params, labels = r2.results(labels_pinned)
             ctx.synchronize()
             barrier()
             dt = time.perf_counter() - t0
@@ -435,7 +436,7 @@ def main():
         e2e = {"value": n_total * k * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                "fit_seconds": dt, "iterations": args.steps,
                "what": "one whole fit through the C-ABI from pinned host memory: upload of the rank's points, initialisation, "
-                       f"{args.steps} iterations each reading back the convergence scalars, parameters and N labels downloaded; "
+                       f"{args.steps} iterations each reading back the convergence scalars, parameters and N labels downloaded (labels into a pinned buffer); "
                        "bytes are per iteration (totals / iterations)",
                "last_scalar": last_e2e}
         if kind == "em" and args.steps - 1 >= args.warmup:

@@ -329,10 +329,15 @@ class Em:
         check(lib().mlb_em_get_precisions(self._h, _ptr(inv), _ptr(sd)))
         return inv.transpose(0, 2, 1).copy(), sd
 
-    def emit(self, want_responsibilities=True, want_labels=True, rows=None):
+    def emit(self, want_responsibilities=True, want_labels=True, rows=None, labels_out=None):
+        """`labels_out`: an optional caller-owned uint32 array of n_local entries to receive the labels (e.g. pinned
+        host memory, which the library copies into directly instead of through its bounce buffers)."""
         n = self.n_local if rows is None else rows
         resp = np.empty((n, self.k), order="F") if want_responsibilities else None
-        labels = np.empty(n, dtype=np.uint32) if want_labels else None
+        labels = None
+        if want_labels:
+            labels = np.empty(n, dtype=np.uint32) if labels_out is None else labels_out
+            assert labels.dtype == np.uint32 and labels.shape == (n,) and labels.flags.c_contiguous
         check(lib().mlb_em_emit(self._h, _ptr(resp), n, _ptr(labels)))
         return resp, labels
 
@@ -409,8 +414,9 @@ class Km:
         check(lib().mlb_km_predict(self._h, _ptr(pts), m, self.d, _ptr(labels), _ptr(dist)))
         return labels, dist
 
-    def get_labels(self):
-        labels = np.empty(self.n_local, dtype=np.uint32)
+    def get_labels(self, labels_out=None):
+        labels = np.empty(self.n_local, dtype=np.uint32) if labels_out is None else labels_out
+        assert labels.dtype == np.uint32 and labels.shape == (self.n_local,) and labels.flags.c_contiguous
         check(lib().mlb_km_get_labels(self._h, _ptr(labels)))
         return labels
 
