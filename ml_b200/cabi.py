@@ -341,6 +341,14 @@ class Em:
         check(lib().mlb_em_emit(self._h, _ptr(resp), n, _ptr(labels)))
         return resp, labels
 
+    def emit_range(self, begin, count, want_labels=True):
+        """Responsibilities (count, K) and labels of the global point range [begin, begin + count) at the parameters the
+        last step's E-step used."""
+        resp = np.empty((count, self.k), order="F")
+        labels = np.empty(count, dtype=np.uint32) if want_labels else None
+        check(lib().mlb_em_emit_range(self._h, begin, count, _ptr(resp), max(count, 1), _ptr(labels)))
+        return resp, labels
+
     def set_kernel_timing(self, enabled):
         check(lib().mlb_em_set_kernel_timing(self._h, int(enabled)))
 
