@@ -134,19 +134,29 @@ def test_em_c2_at_full_size_against_a_numpy_iteration(cabi, ctx):
     em.close(), data.close()
 
 
-def test_em_c3_share_at_full_size_through_moment_identities(cabi, ctx):
-    """The per-GPU share of C3 (N = 12.5M, D = 16, K = 32).  Every row of responsibilities sums to one, so the M-step's
-    outputs must recombine to plain sums over the data, whatever the responsibilities are:
+@pytest.mark.parametrize("gpus", [1, 8])
+def test_em_c3_at_full_size_through_moment_identities(cabi, gpus):
+    """C3 (D = 16, K = 32) with 12.5M points per GPU: the per-GPU share on one GPU, and the north-star configuration as
+    quoted, N = 100M point-sharded over 8 GPUs of one process, when the box has them.  Every row of responsibilities
+    sums to one, so the M-step's outputs must recombine to plain sums over the data, whatever the responsibilities are:
         sum_k s_k = N,   sum_k s_k mu_k = sum_i x_i,   sum_k s_k (Sigma_k - 1e-15 I + mu_k mu_k^T) = sum_i x_i x_i^T,
-    which checks that every point (ragged tail included) entered the statistics exactly once; sampled rows of the
-    responsibilities are recomputed on the host."""
-    n, d, k = 12_500_000, 16, 32
+    which checks that every point of every shard (ragged tail included) entered the statistics exactly once; sampled
+    rows of the responsibilities are recomputed on the host."""
+    if cabi.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    n, d, k = 12_500_000 * gpus, 16, 32
+    ctx = cabi.Context(gpus)
     data, em, before, ll_next, (means, covs, weights) = _start(cabi, ctx, n, d, k)
     x = _download_all(data, n)
     centre = x[: 1 << 16].mean(axis=0)
-    z = x - centre
-    first = z.sum(axis=0) / n
-    second = (z.T @ z) / n
+    first = np.zeros(d)
+    second = np.zeros((d, d))
+    for lo in range(0, n, 1 << 22):
+        z = x[lo:lo + (1 << 22)] - centre
+        first += z.sum(axis=0)
+        second += z.T @ z
+    first /= n
+    second /= n
     mu = means.T - centre                                        # (K, D), about the same point
     got_first = weights @ mu
     got_second = sum(weights[c] * (covs[c] - 1e-15 * np.eye(d) + np.outer(mu[c], mu[c])) for c in range(k))
@@ -159,7 +169,7 @@ def test_em_c3_share_at_full_size_through_moment_identities(cabi, ctx):
     assert np.max(np.abs(got_head - head)) <= 1e-9 and np.max(np.abs(got_tail - tail)) <= 1e-9
     clear = np.sort(head, axis=1)[:, -1] - np.sort(head, axis=1)[:, -2] > 1e-6
     assert np.array_equal(lab_head[clear], np.argmax(head, axis=1)[clear].astype(np.uint32))
-    em.close(), data.close()
+    em.close(), data.close(), ctx.close()
 
 
 def test_kmeans_at_full_size(cabi, ctx):
