@@ -197,6 +197,7 @@ int mlb_em_launch_count(const mlb_em* em, int64_t* launches);
 
 /* ---------------------------------------------------------------- K-means (ML/KMeans.cpp) */
 
+/* D <= 64; any K (centroids that do not fit one CTA's shared memory are processed in blocks, same results). */
 int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out);
 int mlb_km_destroy(mlb_km* km);
 

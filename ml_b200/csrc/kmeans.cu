@@ -41,7 +41,10 @@ struct KmArgs {
     double* partials;       // [n_chunks][SV]: K x (D+1) sums and counts, inertia, changed
     int chunk, n_chunks;
     unsigned* counter;
-    double* dist_out;       // optional: the squared distance of every point to its centroid (mlb_km_predict)
+    double* dist_out;       // optional: the squared distance of every point to its centroid (mlb_km_predict, centroid blocks)
+    int pstride;            // doubles between the partial vectors of consecutive chunks
+    int poff;               // assignment: where a chunk's 8 scalars (inertia, changed, ...) start inside its partial
+    int k_lo;               // statistics: first cluster of the block this launch accumulates (KP clusters from k_lo)
 };
 
 __device__ __forceinline__ void km_dmma(double (&acc)[2], double a, double b)
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
 {
     constexpr int DQ = DP / 4, XS = DP + 4;
     extern __shared__ __align__(16) double sm[];
-    const int KP = p.KP, d = p.d, SD = d + 1;
+    const int KP = p.KP, d = p.d;
     double* Bf = sm;                                  // DP * KP
     double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
     double* Xb = nrm + KP;                            // [4 warps][2 buffers][16][XS], raw coordinates (padding columns zero)
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
         }
 
         // ---------------- the chunk's inertia and changed-label count: fixed order inside the warp and across the warps
-        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        double* out = p.partials + static_cast<long long>(chunk) * p.pstride + p.poff;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, off);
@@ -330,10 +333,10 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
         if (lane == 0) { red[warp] = inertia_acc; red[8 + warp] = static_cast<double>(changed_acc); }
         __syncthreads();
         if (tid == 0) {
-            out[KP * SD] = (red[0] + red[1]) + (red[2] + red[3]);
-            out[KP * SD + 1] = (red[8] + red[9]) + (red[10] + red[11]);
+            out[0] = (red[0] + red[1]) + (red[2] + red[3]);
+            out[1] = (red[8] + red[9]) + (red[10] + red[11]);
         }
-        if (tid >= 2 && tid < 8) out[KP * SD + tid] = 0.0;
+        if (tid >= 2 && tid < 8) out[tid] = 0.0;
     }
 }
 
@@ -386,7 +389,8 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
                 const int e = tid + u * kStThreads;
                 xr[u] = e < nel ? __ldg(xg + e) : 0.0;
             }
-            if (tid < kStTile) lr = tid < nvalid ? static_cast<int>(p.labels[tile0 + tid]) : -1;
+            // labels relative to the cluster block of this launch; anything outside [0, KP) belongs to another block
+            if (tid < kStTile) lr = tid < nvalid ? static_cast<int>(p.labels[tile0 + tid]) - p.k_lo : -1;
         };
         prefetch(0);
         for (int t = 0; t < ntiles; ++t) {
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
         if (reg_counts && lane < KP / 8) sums[static_cast<size_t>(own_lo + lane) * SD + d] = cnt;
         cnt = 0.0;
         __syncthreads();
-        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        double* out = p.partials + static_cast<long long>(chunk) * p.pstride + static_cast<long long>(p.k_lo) * SD;
         for (int i = tid; i < KP * SD; i += kStThreads) {
             out[i] = sums[i];
             sums[i] = 0.0;
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(kKmThreads) km_stats_small_kernel(const KmArgs
             }
         }
         __syncthreads();
-        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, p.KP);
+        double* out = p.partials + static_cast<long long>(chunk) * p.pstride;
         for (int i = tid; i < p.KP * SD; i += kKmThreads) {
             const int kk = i / SD, col = i - kk * SD;
             out[i] = redbuf[kk * (8 * NTD) + col];
@@ -612,6 +616,54 @@ __global__ void km_scalars_kernel(const double* vsum, int SV, int base, double* 
     out[2] = tree8(vsum + base + 1, SV);
 }
 
+// ---------------------------------------------------------------- centroid blocks (K beyond one CTA's shared memory)
+// The centroids are cut into blocks of KB that fit; the assignment kernel runs once per block and leaves every point's
+// nearest centroid WITHIN the block (lowest index on ties) and its exactly evaluated squared distance.  Folding the
+// blocks in ascending order with a strict < is the reference's scan over all K (KMeans.cpp:153-165): same label, same
+// distance.
+__global__ void km_combine_kernel(const unsigned* __restrict__ block_labels, const double* __restrict__ block_dist, long long n, unsigned base, int first,
+                                  unsigned* __restrict__ best_labels, double* __restrict__ best_dist)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dist = block_dist[i];
+    if (first || dist < best_dist[i]) {
+        best_dist[i] = dist;
+        best_labels[i] = base + block_labels[i];
+    }
+}
+
+// After the last block: labels <- winners, and per chunk the inertia and the number of changed labels, added in a fixed
+// order (a thread adds its points in index order, then a fixed tree over the 256 threads).  One CTA per chunk.
+__global__ void __launch_bounds__(256) km_finish_assign_kernel(const unsigned* __restrict__ best_labels, const double* __restrict__ best_dist, long long n, int chunk,
+                                                               unsigned* __restrict__ labels, double* __restrict__ partials, int pstride, int poff)
+{
+    __shared__ double part[256];
+    __shared__ double changed[256];
+    const long long p_begin = static_cast<long long>(blockIdx.x) * chunk;
+    const long long p_end = p_begin + chunk < n ? p_begin + chunk : n;
+    double acc = 0.0, ch = 0.0;
+    for (long long i = p_begin + threadIdx.x; i < p_end; i += 256) {
+        const unsigned now = best_labels[i];
+        acc += best_dist[i];
+        if (labels[i] != now) ch += 1.0;
+        labels[i] = now;
+    }
+    part[threadIdx.x] = acc;
+    changed[threadIdx.x] = ch;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (static_cast<int>(threadIdx.x) < s) {
+            part[threadIdx.x] += part[threadIdx.x + s];
+            changed[threadIdx.x] += changed[threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    double* out = partials + static_cast<long long>(blockIdx.x) * pstride + poff;
+    if (threadIdx.x == 0) { out[0] = part[0]; out[1] = changed[0]; }
+    if (threadIdx.x >= 2 && threadIdx.x < 8) out[threadIdx.x] = 0.0;
+}
+
 using KmKernelFn = void (*)(KmArgs);
 
 static KmKernelFn km_kernel_for(int DP)
@@ -662,6 +714,12 @@ struct KmGpu {
     unsigned* counter = nullptr;
     int grid = 0, grid_stats = 0;
     KernelTimer timer;
+    // centroid blocks (nblocks > 1): per-point winners so far and the current block's results; 8 scalars per chunk
+    unsigned* best_lab = nullptr;
+    double* best_dist = nullptr;
+    unsigned* lab_tmp = nullptr;
+    double* dist_tmp = nullptr;
+    double* scratch = nullptr;
 };
 
 }  // namespace mlb
@@ -672,6 +730,7 @@ struct mlb_km {
     mlb_ctx* ctx = nullptr;
     mlb_data* data = nullptr;
     int d = 0, k = 0, DP = 0, KP = 0, SV = 0;
+    int KB = 0, nblocks = 1;     // centroid blocks: KP = nblocks * KB; one block (KB == KP) whenever K fits shared memory
     std::vector<KmGpu> gpus;
     KmKernelFn fn = nullptr, fn_stats = nullptr;
     bool stats_small = false;
@@ -686,14 +745,63 @@ static int km_prepare(mlb_km* km)
 {
     return for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
         KmGpu& kg = km->gpus[g];
-        KmPrepArgs a{kg.craw, km->data->shards[g].shift, km->d, km->k, km->DP, km->KP, kg.cfrag, kg.cnorm, kg.cmax};
-        km_prepare_kernel<<<(km->KP + 127) / 128, 128, 0, gpu.stream>>>(a);
-        MLB_CUDA(cudaGetLastError());
-        km_cmax_kernel<<<1, 1, 0, gpu.stream>>>(kg.cnorm, km->k, kg.cmax);
-        MLB_CUDA(cudaGetLastError());
-        km->launches += 2;
+        for (int b = 0; b < km->nblocks; ++b) {
+            const int k_b = std::min(km->KB, km->k - b * km->KB);
+            KmPrepArgs a{kg.craw + static_cast<size_t>(b) * km->KB * km->d, km->data->shards[g].shift, km->d, k_b, km->DP, km->KB,
+                         kg.cfrag + static_cast<size_t>(b) * km->DP * km->KB, kg.cnorm + static_cast<size_t>(b) * km->KB, kg.cmax + b};
+            km_prepare_kernel<<<(km->KB + 127) / 128, 128, 0, gpu.stream>>>(a);
+            MLB_CUDA(cudaGetLastError());
+            km_cmax_kernel<<<1, 1, 0, gpu.stream>>>(a.cnorm, k_b, a.cmax);
+            MLB_CUDA(cudaGetLastError());
+            km->launches += 2;
+        }
         return MLB_OK;
     });
+}
+
+// The assignment of n points at x (device memory of local GPU g): labels (in: the previous labels, out: the new ones),
+// per chunk the inertia and the number of changed labels at partials[chunk * pstride + poff], optionally every point's
+// squared distance.  One launch when the centroids are one block; otherwise one launch per block into per-point
+// temporaries (tmp_*: n entries each, owned by the caller), folded in ascending block order.
+static int launch_assign(mlb_km* km, int g, const double* x, long long n, int chunk, int n_chunks, unsigned* labels, double* dist_out, double* partials,
+                         int pstride, int poff, unsigned* tmp_best_lab, double* tmp_best_dist, unsigned* tmp_lab, double* tmp_dist, double* tmp_scratch)
+{
+    Gpu& gpu = km->ctx->gpus[g];
+    KmGpu& kg = km->gpus[g];
+    KmArgs a{};
+    a.x = x; a.n_local = n; a.d = km->d; a.KP = km->KB;
+    a.shift = km->data->shards[g].shift;
+    a.chunk = chunk; a.n_chunks = n_chunks;
+    a.counter = kg.counter;
+    if (km->nblocks == 1) {
+        a.k = km->k;
+        a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
+        a.labels = labels; a.partials = partials; a.pstride = pstride; a.poff = poff; a.dist_out = dist_out;
+        MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+        km->fn<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        ++km->launches;
+        return MLB_OK;
+    }
+    double* best_dist = dist_out ? dist_out : tmp_best_dist;
+    for (int b = 0; b < km->nblocks; ++b) {
+        a.k = std::min(km->KB, km->k - b * km->KB);
+        a.cfrag = kg.cfrag + static_cast<size_t>(b) * km->DP * km->KB;
+        a.cnorm = kg.cnorm + static_cast<size_t>(b) * km->KB;
+        a.craw = kg.craw + static_cast<size_t>(b) * km->KB * km->d;
+        a.cmax = kg.cmax + b;
+        a.labels = tmp_lab; a.partials = tmp_scratch; a.pstride = 8; a.poff = 0; a.dist_out = tmp_dist;
+        MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+        km->fn<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        km_combine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, gpu.stream>>>(tmp_lab, tmp_dist, n, static_cast<unsigned>(b) * km->KB, b == 0, tmp_best_lab, best_dist);
+        MLB_CUDA(cudaGetLastError());
+        km->launches += 2;
+    }
+    km_finish_assign_kernel<<<n_chunks, 256, 0, gpu.stream>>>(tmp_best_lab, best_dist, n, chunk, labels, partials, pstride, poff);
+    MLB_CUDA(cudaGetLastError());
+    ++km->launches;
+    return MLB_OK;
 }
 
 }  // namespace mlb
@@ -710,13 +818,33 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
     for (int cand : {4, 8, 16, 32, 64})
         if (d <= cand) { DP = cand; break; }
     MLB_REQUIRE(DP, "mlb_km_create: D=%d not supported by this build (D <= 64)", d);
-    const int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup;
-    const size_t smem = km_smem_bytes(DP, KP), smem_stats = (KP == kKmGroup && DP <= 32) ? km_stats_small_smem_bytes(DP) : km_stats_smem_bytes(d, KP);
-    MLB_REQUIRE(std::max(smem, smem_stats) <= 227 * 1024, "mlb_km_create: D=%d, K=%d needs %zu bytes of shared memory (limit 232448)", d, k, std::max(smem, smem_stats));
+    constexpr size_t kSmemLimit = 227 * 1024;
+    int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup, KB = KP, nblocks = 1;
+    auto stats_bytes = [&](int kp) { return (kp == kKmGroup && DP <= 32) ? km_stats_small_smem_bytes(DP) : km_stats_smem_bytes(d, kp); };
+    int forced = 0;   // MLB200_KM_BLOCK: developer override (a multiple of 32) that forces small centroid blocks, for tests
+    if (const char* env = std::getenv("MLB200_KM_BLOCK")) forced = std::atoi(env) / kKmGroup * kKmGroup;
+    if (std::max(km_smem_bytes(DP, KP), stats_bytes(KP)) > kSmemLimit || (forced >= kKmGroup && forced < KP)) {
+        // Centroid blocks: the largest block that leaves room for two CTAs per SM if that is at least 128 centroids,
+        // else the largest that fits at all.
+        auto largest = [&](size_t limit) {
+            int kb = 0;
+            for (int cand = kKmGroup; cand <= 4096; cand += kKmGroup)
+                if (km_smem_bytes(DP, cand) <= limit && km_stats_smem_bytes(d, cand) <= kSmemLimit) kb = cand;
+            return kb;
+        };
+        KB = largest(kSmemLimit / 2 - 1024);
+        if (KB < 128) KB = largest(kSmemLimit);
+        if (forced >= kKmGroup) KB = std::min(KB, forced);
+        MLB_REQUIRE(KB >= kKmGroup, "mlb_km_create: D=%d leaves no room for a block of centroids in shared memory", d);
+        nblocks = (k + KB - 1) / KB;
+        KP = nblocks * KB;
+    }
+    const size_t smem = km_smem_bytes(DP, KB), smem_stats = nblocks == 1 ? stats_bytes(KB) : km_stats_smem_bytes(d, KB);
     auto* km = new mlb_km;
     km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->SV = km_sv(d, KP);
+    km->KB = KB; km->nblocks = nblocks;
     km->fn = km_kernel_for(DP);
-    km->stats_small = KP == kKmGroup && DP <= 32;   // K <= 32: one-hot tensor-pipe statistics (its accumulators fit the registers up to D = 32)
+    km->stats_small = nblocks == 1 && KP == kKmGroup && DP <= 32;   // K <= 32: one-hot tensor-pipe statistics (its accumulators fit the registers up to D = 32)
     km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : km_stats_kernel_for(DP);
     km->smem = smem;
     km->smem_stats = smem_stats;
@@ -728,7 +856,16 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         MLB_CUDA(cudaMallocAsync(&kg.cold, sizeof(double) * d * k, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&kg.cfrag, sizeof(double) * DP * KP, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&kg.cnorm, sizeof(double) * KP, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.cmax, sizeof(double), gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&kg.cmax, sizeof(double) * km->nblocks, gpu.stream));
+        if (km->nblocks > 1) {
+            const int64_t n = std::max<int64_t>(1, sh.n());
+            MLB_CUDA(cudaMallocAsync(&kg.best_lab, sizeof(unsigned) * n, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&kg.best_dist, sizeof(double) * n, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&kg.lab_tmp, sizeof(unsigned) * n, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&kg.dist_tmp, sizeof(double) * n, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&kg.scratch, sizeof(double) * 8 * std::max<int64_t>(1, sh.n_chunks()), gpu.stream));
+            MLB_CUDA(cudaMemsetAsync(kg.lab_tmp, 0, sizeof(unsigned) * n, gpu.stream));
+        }
         MLB_CUDA(cudaMallocAsync(&kg.labels, sizeof(unsigned) * std::max<int64_t>(1, sh.n()), gpu.stream));
         MLB_CUDA(cudaMallocAsync(&kg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&kg.vsum, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
@@ -765,7 +902,8 @@ int mlb_km_destroy(mlb_km* km)
         kg.timer.destroy();
         for (void* ptr : {static_cast<void*>(kg.craw), static_cast<void*>(kg.cold), static_cast<void*>(kg.cfrag), static_cast<void*>(kg.cnorm),
                           static_cast<void*>(kg.cmax), static_cast<void*>(kg.labels), static_cast<void*>(kg.partials), static_cast<void*>(kg.vsum),
-                          static_cast<void*>(kg.out), static_cast<void*>(kg.counter)})
+                          static_cast<void*>(kg.out), static_cast<void*>(kg.counter), static_cast<void*>(kg.best_lab), static_cast<void*>(kg.best_dist),
+                          static_cast<void*>(kg.lab_tmp), static_cast<void*>(kg.dist_tmp), static_cast<void*>(kg.scratch)})
             if (ptr) cudaFreeAsync(ptr, km->ctx->gpus[g].stream);
     }
     delete km;
@@ -805,22 +943,24 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         KmGpu& kg = km->gpus[g];
         const DataShard& sh = km->data->shards[g];
-        KmArgs a{};
-        a.x = sh.x; a.n_local = sh.n(); a.d = km->d; a.k = km->k; a.KP = km->KP;
-        a.shift = sh.shift; a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
-        a.labels = kg.labels; a.partials = kg.partials;
-        a.chunk = km->data->lay.chunk; a.n_chunks = static_cast<int>(sh.n_chunks());
-        a.counter = kg.counter;
-        MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-        if (a.n_chunks > 0) {
+        const int chunk = km->data->lay.chunk, n_chunks = static_cast<int>(sh.n_chunks());
+        if (n_chunks > 0) {
             MLB_TRY(kg.timer.begin(gpu.stream));
-            km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
-            MLB_CUDA(cudaGetLastError());
-            MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-            km->fn_stats<<<std::min(kg.grid_stats, a.n_chunks), km->stats_small ? kKmThreads : kStThreads, km->smem_stats, gpu.stream>>>(a);
-            MLB_CUDA(cudaGetLastError());
+            MLB_TRY(launch_assign(km, g, sh.x, sh.n(), chunk, n_chunks, kg.labels, nullptr, kg.partials, km->SV, km->KP * (km->d + 1),
+                                  kg.best_lab, kg.best_dist, kg.lab_tmp, kg.dist_tmp, kg.scratch));
+            // statistics of the fresh labels, one launch per centroid block
+            KmArgs a{};
+            a.x = sh.x; a.n_local = sh.n(); a.d = km->d; a.k = km->k; a.KP = km->KB;
+            a.shift = sh.shift; a.labels = kg.labels; a.partials = kg.partials; a.pstride = km->SV;
+            a.chunk = chunk; a.n_chunks = n_chunks; a.counter = kg.counter;
+            for (int b = 0; b < km->nblocks; ++b) {
+                a.k_lo = b * km->KB;
+                MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+                km->fn_stats<<<std::min(kg.grid_stats, n_chunks), km->stats_small ? kKmThreads : kStThreads, km->smem_stats, gpu.stream>>>(a);
+                MLB_CUDA(cudaGetLastError());
+                ++km->launches;
+            }
             MLB_TRY(kg.timer.end(gpu.stream));
-            km->launches += 2;
         }
         return MLB_OK;
     }));
@@ -874,35 +1014,32 @@ int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigne
     if (!km->have_centroids) { set_error("mlb_km_predict: centroids not set"); return MLB_ESTATE; }
     if (m == 0) return MLB_OK;
     constexpr int64_t kStage = 1 << 20;   // points per staged batch
-    constexpr int kChunk = 2048;          // the assignment kernel writes one (unused here) inertia partial per chunk
+    constexpr int kChunk = 2048;          // the assignment kernel leaves one (unused here) inertia partial per chunk
     Gpu& gpu = km->ctx->gpus[0];
-    KmGpu& kg = km->gpus[0];
     const int d = km->d;
     MLB_CUDA(cudaSetDevice(gpu.device));
     const int64_t cap = std::min<int64_t>(m, kStage);
-    double *xd = nullptr, *dist = nullptr, *partials = nullptr;
-    unsigned* labels = nullptr;
+    const int64_t cap_chunks = (cap + kChunk - 1) / kChunk;
+    double *xd = nullptr, *dist = nullptr, *partials = nullptr, *tmp_dist = nullptr, *tmp_scratch = nullptr;
+    unsigned *labels = nullptr, *tmp_best_lab = nullptr, *tmp_lab = nullptr;
     auto body = [&]() -> int {
         MLB_CUDA(cudaMallocAsync(&xd, sizeof(double) * cap * d, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&dist, sizeof(double) * cap, gpu.stream));
         MLB_CUDA(cudaMallocAsync(&labels, sizeof(unsigned) * cap, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&partials, sizeof(double) * ((cap + kChunk - 1) / kChunk) * km->SV, gpu.stream));
+        MLB_CUDA(cudaMallocAsync(&partials, sizeof(double) * 8 * cap_chunks, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(labels, 0, sizeof(unsigned) * cap, gpu.stream));   // the kernel reads the "previous" labels
+        if (km->nblocks > 1) {
+            MLB_CUDA(cudaMallocAsync(&tmp_best_lab, sizeof(unsigned) * cap, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&tmp_lab, sizeof(unsigned) * cap, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&tmp_dist, sizeof(double) * cap, gpu.stream));
+            MLB_CUDA(cudaMallocAsync(&tmp_scratch, sizeof(double) * 8 * cap_chunks, gpu.stream));
+            MLB_CUDA(cudaMemsetAsync(tmp_lab, 0, sizeof(unsigned) * cap, gpu.stream));
+        }
         for (int64_t off = 0; off < m; off += kStage) {
             const int64_t n = std::min<int64_t>(kStage, m - off);
-            const double* src = x + off * ld_x;
-            MLB_TRY(staged_h2d(gpu, xd, src, static_cast<size_t>(n), sizeof(double) * d, sizeof(double) * ld_x));
-            KmArgs a{};
-            a.x = xd; a.n_local = n; a.d = d; a.k = km->k; a.KP = km->KP;
-            a.shift = km->data->shards[0].shift; a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
-            a.labels = labels; a.partials = partials;
-            a.chunk = kChunk; a.n_chunks = static_cast<int>((n + kChunk - 1) / kChunk);
-            a.counter = kg.counter;
-            a.dist_out = dist;
-            MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-            km->fn<<<std::min(kg.grid, a.n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
-            MLB_CUDA(cudaGetLastError());
-            ++km->launches;
+            MLB_TRY(staged_h2d(gpu, xd, x + off * ld_x, static_cast<size_t>(n), sizeof(double) * d, sizeof(double) * ld_x));
+            MLB_TRY(launch_assign(km, 0, xd, n, kChunk, static_cast<int>((n + kChunk - 1) / kChunk), labels, dist, partials, 8, 0,
+                                  tmp_best_lab, nullptr, tmp_lab, tmp_dist, tmp_scratch));
             MLB_TRY(staged_d2h(gpu, labels_out + off, labels, sizeof(unsigned) * n));
             if (sqdist_out) MLB_TRY(staged_d2h(gpu, sqdist_out + off, dist, sizeof(double) * n));
             MLB_CUDA(cudaStreamSynchronize(gpu.stream));
@@ -910,7 +1047,8 @@ int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigne
         return MLB_OK;
     };
     const int rc = body();
-    for (void* ptr : {static_cast<void*>(xd), static_cast<void*>(dist), static_cast<void*>(labels), static_cast<void*>(partials)})
+    for (void* ptr : {static_cast<void*>(xd), static_cast<void*>(dist), static_cast<void*>(labels), static_cast<void*>(partials), static_cast<void*>(tmp_best_lab),
+                      static_cast<void*>(tmp_lab), static_cast<void*>(tmp_dist), static_cast<void*>(tmp_scratch)})
         if (ptr) cudaFreeAsync(ptr, gpu.stream);
     return rc;
 }

@@ -253,3 +253,52 @@ def test_kmeans_duplicate_centroids_take_the_exact_path(ctx):
     assert got.iterations == ref.iterations
     assert np.array_equal(got.labels, ref.labels)
     assert rel_err(got.centroids, ref.centroids) <= RTOL
+
+
+# ---------------------------------------------------------------- K beyond one CTA's shared memory: centroid blocks
+
+def _kmeans_blocked_case(ctx, n, d, k, seed, steps=12):
+    from ml_b200 import cabi
+    data, _, _ = synthetic_gmm(n, d, max(2, k // 10), seed=seed, spread=6.0)
+    init = np.ascontiguousarray(data[:: max(1, n // k)][:k].T)
+    ref = oracle.kmeans_fit(data, k, init=oracle.EXPLICIT, explicit_means=init, maximum_steps=steps)
+    dev = cabi.Data.upload(ctx, data)
+    km = cabi.Km(dev, k)
+    km.set_centroids(init)
+    iterations, converged, inertia = 0, False, 0.0
+    for step in range(steps):
+        inertia, changed = km.assign()
+        iterations = step + 1
+        if step > 0 and changed == 0:
+            converged = True
+            break
+        shift = km.update()
+        if step > 0 and shift < 1e-8:
+            inertia, changed = km.assign()
+            converged = True
+            break
+    assert iterations == ref.iterations and converged == ref.converged
+    assert np.array_equal(km.get_labels(), ref.labels)
+    assert abs(inertia - ref.inertia) <= RTOL * ref.inertia
+    assert rel_err(km.get_centroids(), ref.centroids) <= RTOL
+    queries = np.ascontiguousarray(data[:300] + 0.5)
+    labels, dist = km.predict(queries)
+    want = [oracle.kmeans_assign_label(km.get_centroids(), q) for q in queries]
+    assert np.array_equal(labels, np.array([w[0] for w in want], dtype=np.uint32))
+    assert np.max(np.abs(dist - np.array([w[1] for w in want])) / np.array([w[1] for w in want])) <= 1e-13
+    km.close()
+    dev.close()
+
+
+@pytest.mark.parametrize("n,d,k,seed", [(20000, 32, 1000, 71), (12000, 64, 700, 72), (9000, 13, 2100, 73)])
+def test_kmeans_with_more_centroids_than_shared_memory_holds(ctx, n, d, k, seed):
+    """The centroids are cut into blocks that fit; folding the blocks' exact winners in ascending order with a strict <
+    is the reference's scan over all K (KMeans.cpp:153-165): identical labels, iteration count and distances."""
+    _kmeans_blocked_case(ctx, n, d, k, seed)
+
+
+@pytest.mark.parametrize("n,d,k,block", [(7000, 5, 200, 64), (5000, 2, 70, 32), (6001, 32, 256, 96)])
+def test_kmeans_forced_small_centroid_blocks(ctx, monkeypatch, n, d, k, block):
+    """The same path with small blocks forced (MLB200_KM_BLOCK), including a ragged last block."""
+    monkeypatch.setenv("MLB200_KM_BLOCK", str(block))
+    _kmeans_blocked_case(ctx, n, d, k, seed=n + k)
