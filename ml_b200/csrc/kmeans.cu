@@ -42,8 +42,7 @@ struct KmArgs {
     int chunk, n_chunks;
     unsigned* counter;
     double* dist_out;       // optional: the squared distance of every point to its centroid (mlb_km_predict, centroid blocks)
-    int pstride;            // doubles between the partial vectors of consecutive chunks
-    int poff;               // assignment: where a chunk's 8 scalars (inertia, changed, ...) start inside its partial
+    int pstride;            // statistics: doubles between the partial vectors of consecutive chunks
     int k_lo;               // statistics: first cluster of the block this launch accumulates (KP clusters from k_lo)
 };
 
@@ -108,12 +107,15 @@ __device__ __forceinline__ void km_cp_async_wait() { asm volatile("cp.async.wait
 // exact refinement of one warp (global loads of centroid rows) overlaps the tensor-pipe filter of the others.
 constexpr int kKmSub = 16;   // points per warp sub-tile
 
-template <int DP>
+// COMPACT: the chunk's 8 scalars go to partials[chunk * 8] (centroid blocks, prediction) instead of to their slots in the
+// chunk's full statistics vector.  A template parameter, not run-time addressing: with the addressing made generic ptxas
+// allocates the main loop differently (125 instead of 149 registers at D = 32) and the kernel is 5 % slower on C5.
+template <int DP, bool COMPACT>
 __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
 {
     constexpr int DQ = DP / 4, XS = DP + 4;
     extern __shared__ __align__(16) double sm[];
-    const int KP = p.KP, d = p.d;
+    const int KP = p.KP, d = p.d, SD = d + 1;
     double* Bf = sm;                                  // DP * KP
     double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
     double* Xb = nrm + KP;                            // [4 warps][2 buffers][16][XS], raw coordinates (padding columns zero)
@@ -317,14 +319,14 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
                     inertia_acc += d2;
                     if (old_labels[pl] != static_cast<unsigned>(label)) ++changed_acc;
                     p.labels[tile0 + pl] = static_cast<unsigned>(label);
-                    if (p.dist_out) p.dist_out[tile0 + pl] = d2;
+                    if (COMPACT && p.dist_out) p.dist_out[tile0 + pl] = d2;
                 }
             }
             __syncwarp();   // the buffer and the verdicts are rewritten two sub-tiles later / by the next sub-tile
         }
 
         // ---------------- the chunk's inertia and changed-label count: fixed order inside the warp and across the warps
-        double* out = p.partials + static_cast<long long>(chunk) * p.pstride + p.poff;
+        double* out = COMPACT ? p.partials + static_cast<long long>(chunk) * 8 - KP * SD : p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, off);
@@ -333,10 +335,10 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
         if (lane == 0) { red[warp] = inertia_acc; red[8 + warp] = static_cast<double>(changed_acc); }
         __syncthreads();
         if (tid == 0) {
-            out[0] = (red[0] + red[1]) + (red[2] + red[3]);
-            out[1] = (red[8] + red[9]) + (red[10] + red[11]);
+            out[KP * SD] = (red[0] + red[1]) + (red[2] + red[3]);
+            out[KP * SD + 1] = (red[8] + red[9]) + (red[10] + red[11]);
         }
-        if (tid >= 2 && tid < 8) out[tid] = 0.0;
+        if (tid >= 2 && tid < 8) out[KP * SD + tid] = 0.0;
     }
 }
 
@@ -346,7 +348,9 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
 // reproducible.  A separate kernel (it re-reads the points and the fresh labels, 8D + 4 bytes per point, a few percent
 // of the assignment's time) so that the assignment kernel keeps its shared memory for the centroids and runs several
 // CTAs per SM.
-template <int DP>
+// BLOCKED: the launch accumulates the KP clusters from p.k_lo on (centroid blocks) into their slots of the chunk's full
+// statistics vector; a template parameter so that the one-block kernel stays exactly the measured one.
+template <int DP, bool BLOCKED>
 __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
 {
     constexpr int XR = kStTile * DP / kStThreads;   // coordinates of the next tile each thread holds in registers
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
                 xr[u] = e < nel ? __ldg(xg + e) : 0.0;
             }
             // labels relative to the cluster block of this launch; anything outside [0, KP) belongs to another block
-            if (tid < kStTile) lr = tid < nvalid ? static_cast<int>(p.labels[tile0 + tid]) - p.k_lo : -1;
+            if (tid < kStTile) lr = tid < nvalid ? static_cast<int>(p.labels[tile0 + tid]) - (BLOCKED ? p.k_lo : 0) : -1;
         };
         prefetch(0);
         for (int t = 0; t < ntiles; ++t) {
@@ -422,7 +426,8 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
         if (reg_counts && lane < KP / 8) sums[static_cast<size_t>(own_lo + lane) * SD + d] = cnt;
         cnt = 0.0;
         __syncthreads();
-        double* out = p.partials + static_cast<long long>(chunk) * p.pstride + static_cast<long long>(p.k_lo) * SD;
+        double* out = BLOCKED ? p.partials + static_cast<long long>(chunk) * p.pstride + static_cast<long long>(p.k_lo) * SD
+                              : p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
         for (int i = tid; i < KP * SD; i += kStThreads) {
             out[i] = sums[i];
             sums[i] = 0.0;
@@ -528,7 +533,7 @@ __global__ void __launch_bounds__(kKmThreads) km_stats_small_kernel(const KmArgs
             }
         }
         __syncthreads();
-        double* out = p.partials + static_cast<long long>(chunk) * p.pstride;
+        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, p.KP);
         for (int i = tid; i < p.KP * SD; i += kKmThreads) {
             const int kk = i / SD, col = i - kk * SD;
             out[i] = redbuf[kk * (8 * NTD) + col];
@@ -666,14 +671,15 @@ __global__ void __launch_bounds__(256) km_finish_assign_kernel(const unsigned* _
 
 using KmKernelFn = void (*)(KmArgs);
 
+template <bool COMPACT>
 static KmKernelFn km_kernel_for(int DP)
 {
     switch (DP) {
-    case 4: return km_assign_kernel<4>;
-    case 8: return km_assign_kernel<8>;
-    case 16: return km_assign_kernel<16>;
-    case 32: return km_assign_kernel<32>;
-    case 64: return km_assign_kernel<64>;
+    case 4: return km_assign_kernel<4, COMPACT>;
+    case 8: return km_assign_kernel<8, COMPACT>;
+    case 16: return km_assign_kernel<16, COMPACT>;
+    case 32: return km_assign_kernel<32, COMPACT>;
+    case 64: return km_assign_kernel<64, COMPACT>;
     default: return nullptr;
     }
 }
@@ -689,14 +695,15 @@ static KmKernelFn km_stats_small_kernel_for(int DP)
     }
 }
 
+template <bool BLOCKED>
 static KmKernelFn km_stats_kernel_for(int DP)
 {
     switch (DP) {
-    case 4: return km_stats_kernel<4>;
-    case 8: return km_stats_kernel<8>;
-    case 16: return km_stats_kernel<16>;
-    case 32: return km_stats_kernel<32>;
-    case 64: return km_stats_kernel<64>;
+    case 4: return km_stats_kernel<4, BLOCKED>;
+    case 8: return km_stats_kernel<8, BLOCKED>;
+    case 16: return km_stats_kernel<16, BLOCKED>;
+    case 32: return km_stats_kernel<32, BLOCKED>;
+    case 64: return km_stats_kernel<64, BLOCKED>;
     default: return nullptr;
     }
 }
@@ -732,7 +739,7 @@ struct mlb_km {
     int d = 0, k = 0, DP = 0, KP = 0, SV = 0;
     int KB = 0, nblocks = 1;     // centroid blocks: KP = nblocks * KB; one block (KB == KP) whenever K fits shared memory
     std::vector<KmGpu> gpus;
-    KmKernelFn fn = nullptr, fn_stats = nullptr;
+    KmKernelFn fn = nullptr, fn_compact = nullptr, fn_stats = nullptr;   // fn_compact: the assignment kernel with compact per-chunk scalars
     bool stats_small = false;
     size_t smem = 0, smem_stats = 0;
     bool have_centroids = false, have_stats = false;
@@ -776,9 +783,11 @@ static int launch_assign(mlb_km* km, int g, const double* x, long long n, int ch
     if (km->nblocks == 1) {
         a.k = km->k;
         a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
-        a.labels = labels; a.partials = partials; a.pstride = pstride; a.poff = poff; a.dist_out = dist_out;
+        a.labels = labels; a.partials = partials; a.dist_out = dist_out;
+        // full statistics vectors (the fit: pstride == SV, scalars at KP * (d + 1)) or 8 scalars per chunk (prediction)
+        const KmKernelFn fn = pstride == 8 ? km->fn_compact : km->fn;
         MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-        km->fn<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+        fn<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
         ++km->launches;
         return MLB_OK;
@@ -790,9 +799,9 @@ static int launch_assign(mlb_km* km, int g, const double* x, long long n, int ch
         a.cnorm = kg.cnorm + static_cast<size_t>(b) * km->KB;
         a.craw = kg.craw + static_cast<size_t>(b) * km->KB * km->d;
         a.cmax = kg.cmax + b;
-        a.labels = tmp_lab; a.partials = tmp_scratch; a.pstride = 8; a.poff = 0; a.dist_out = tmp_dist;
+        a.labels = tmp_lab; a.partials = tmp_scratch; a.dist_out = tmp_dist;
         MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-        km->fn<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+        km->fn_compact<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
         km_combine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, gpu.stream>>>(tmp_lab, tmp_dist, n, static_cast<unsigned>(b) * km->KB, b == 0, tmp_best_lab, best_dist);
         MLB_CUDA(cudaGetLastError());
@@ -843,9 +852,10 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
     auto* km = new mlb_km;
     km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->SV = km_sv(d, KP);
     km->KB = KB; km->nblocks = nblocks;
-    km->fn = km_kernel_for(DP);
+    km->fn = km_kernel_for<false>(DP);
+    km->fn_compact = km_kernel_for<true>(DP);
     km->stats_small = nblocks == 1 && KP == kKmGroup && DP <= 32;   // K <= 32: one-hot tensor-pipe statistics (its accumulators fit the registers up to D = 32)
-    km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : km_stats_kernel_for(DP);
+    km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : nblocks == 1 ? km_stats_kernel_for<false>(DP) : km_stats_kernel_for<true>(DP);
     km->smem = smem;
     km->smem_stats = smem_stats;
     km->gpus.resize(ctx->gpus.size());
@@ -875,6 +885,7 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         MLB_CUDA(cudaMemsetAsync(kg.vsum, 0, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(kg.cold, 0, sizeof(double) * d * k, gpu.stream));
         MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn_compact), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int per_sm = 0, sms = 0;
         MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn), kKmThreads, smem));
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
