@@ -11,6 +11,14 @@
 
 namespace ml
 {
+	/** The matrix views every entry point of this API takes (aliases only: the types, and so the signatures, are the
+	reference's `Eigen::Ref<const Eigen::MatrixXd>`, `Eigen::Ref<Eigen::MatrixXd>` and their vector counterparts). */
+	using DataView = Eigen::Ref<const Eigen::MatrixXd>;
+	using MatrixOut = Eigen::Ref<Eigen::MatrixXd>;
+	using PointView = Eigen::Ref<const Eigen::VectorXd>;
+	using VectorOut = Eigen::Ref<Eigen::VectorXd>;
+	using Prng = std::default_random_engine;
+
 	namespace Clustering
 	{
 		/** A clustering model: fit() on a column-major matrix with one data point per column. */
@@ -24,7 +32,7 @@ namespace ml
 			@return Whether the fit converged.
 			@throw std::invalid_argument If `data` has no rows or fewer columns than clusters.
 			*/
-			virtual bool fit(Eigen::Ref<const Eigen::MatrixXd> data) = 0;
+			virtual bool fit(DataView data) = 0;
 
 			virtual unsigned int number_clusters() const = 0;
 
@@ -49,7 +57,7 @@ namespace ml
 			@param[in] number_components K <= N.
 			@param[out] centroids D x K destination.
 			*/
-			DLL_DECLSPEC virtual void init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids) const = 0;
+			DLL_DECLSPEC virtual void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut centroids) const = 0;
 		};
 
 		/** Chooses initial responsibilities (N x K). */
@@ -58,28 +66,28 @@ namespace ml
 		public:
 			DLL_DECLSPEC virtual ~ResponsibilitiesInitialiser();
 
-			DLL_DECLSPEC virtual void init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> responsibilities) const = 0;
+			DLL_DECLSPEC virtual void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut responsibilities) const = 0;
 		};
 
 		/** K distinct data points drawn without replacement. */
 		class Forgy : public CentroidsInitialiser
 		{
 		public:
-			DLL_DECLSPEC void init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids) const override;
+			DLL_DECLSPEC void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut centroids) const override;
 		};
 
 		/** Means of a uniformly random partition of the points into K groups. */
 		class RandomPartition : public CentroidsInitialiser
 		{
 		public:
-			DLL_DECLSPEC void init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids) const override;
+			DLL_DECLSPEC void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut centroids) const override;
 		};
 
 		/** K-means++ seeding. */
 		class KPP : public CentroidsInitialiser
 		{
 		public:
-			DLL_DECLSPEC void init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids) const override;
+			DLL_DECLSPEC void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut centroids) const override;
 		};
 
 		/** One-hot responsibilities: every point belongs to its nearest initial centroid. */
@@ -89,7 +97,7 @@ namespace ml
 			/** @throw std::invalid_argument If `centroids_initialiser` is null. */
 			DLL_DECLSPEC ClosestCentroid(std::shared_ptr<const CentroidsInitialiser> centroids_initialiser);
 
-			DLL_DECLSPEC void init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> responsibilities) const override;
+			DLL_DECLSPEC void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut responsibilities) const override;
 
 			/** The initialiser the centroids come from (an addition: lets ml::EM run the nearest-centroid pass on the device). */
 			const std::shared_ptr<const CentroidsInitialiser>& centroids_initialiser() const

@@ -62,81 +62,48 @@ namespace ml
 		}
 
 		/** @throw std::invalid_argument If data has no rows or fewer columns than components. */
-		DLL_DECLSPEC bool fit(Eigen::Ref<const Eigen::MatrixXd> data) override;
+		DLL_DECLSPEC bool fit(DataView data) override;
 
-		auto number_components() const
-		{
-			return number_components_;
-		}
+		auto number_components() const { return number_components_; }
 
-		unsigned int number_clusters() const override
-		{
-			return number_components();
-		}
+		unsigned int number_clusters() const override { return number_components(); }
 
 		/** D x K. */
-		const auto& means() const
-		{
-			return means_;
-		}
+		const auto& means() const { return means_; }
 
-		const Eigen::MatrixXd& centroids() const override
-		{
-			return means();
-		}
+		const Eigen::MatrixXd& centroids() const override { return means(); }
 
-		const auto& covariances() const
-		{
-			return covariances_;
-		}
+		const auto& covariances() const { return covariances_; }
 
 		/** @throw std::invalid_argument If k is out of range. */
 		DLL_DECLSPEC const Eigen::MatrixXd& covariance(unsigned int k) const;
 
-		const auto& mixing_probabilities() const
-		{
-			return mixing_probabilities_;
-		}
+		const auto& mixing_probabilities() const { return mixing_probabilities_; }
 
 		/** N x K, from the last E-step of the fit. */
 		DLL_DECLSPEC const Eigen::MatrixXd& responsibilities() const;
 
-		double log_likelihood() const
-		{
-			return log_likelihood_;
-		}
+		double log_likelihood() const { return log_likelihood_; }
 
-		std::shared_ptr<const Clustering::CentroidsInitialiser> means_initialiser() const
-		{
-			return means_initialiser_;
-		}
+		std::shared_ptr<const Clustering::CentroidsInitialiser> means_initialiser() const { return means_initialiser_; }
 
 		/** Responsibilities of the fitted components for a point x (u must have K entries).
 		@throw std::invalid_argument On size mismatch. */
-		DLL_DECLSPEC void assign_responsibilities(Eigen::Ref<const Eigen::VectorXd> x, Eigen::Ref<Eigen::VectorXd> u) const;
+		DLL_DECLSPEC void assign_responsibilities(PointView x, VectorOut u) const;
 
 		/** The same for every column of `points` (D x m) at once, on the device: m x K.
 		@throw std::invalid_argument If `points` has the wrong number of rows.
 		@throw std::logic_error If there is no fitted device state (no fit yet, or the N == K exact fit). */
-		DLL_DECLSPEC Eigen::MatrixXd assign_responsibilities(Eigen::Ref<const Eigen::MatrixXd> points) const;
+		DLL_DECLSPEC Eigen::MatrixXd assign_responsibilities(DataView points) const;
 
-		const std::vector<unsigned int>& labels() const override
-		{
-			return labels_;
-		}
+		const std::vector<unsigned int>& labels() const override { return labels_; }
 
-		bool converged() const override
-		{
-			return converged_;
-		}
+		bool converged() const override { return converged_; }
 
 		/** Iterations (E-step + M-step pairs) executed by the last fit. */
-		unsigned int number_iterations() const
-		{
-			return number_iterations_;
-		}
+		unsigned int number_iterations() const { return number_iterations_; }
 	private:
-		std::default_random_engine prng_;
+		Prng prng_;
 		std::shared_ptr<const Clustering::CentroidsInitialiser> means_initialiser_;
 		std::shared_ptr<const Clustering::ResponsibilitiesInitialiser> responsibilities_initialiser_;
 		Eigen::VectorXd mixing_probabilities_;
@@ -158,7 +125,7 @@ namespace ml
 		bool converged_;
 		mutable std::unique_ptr<detail::EmDevice> device_; /**< HBM-resident state of the last fit */
 
-		void initialise_centroids(const Clustering::CentroidsInitialiser& initialiser, Eigen::Ref<const Eigen::MatrixXd> data, Eigen::Ref<Eigen::MatrixXd> centroids);
+		void initialise_centroids(const Clustering::CentroidsInitialiser& initialiser, DataView data, MatrixOut centroids);
 		void process_covariances(Eigen::Index number_dimensions);
 		void fetch_parameters(Eigen::Index number_dimensions);
 	};

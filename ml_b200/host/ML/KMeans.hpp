@@ -24,22 +24,13 @@ namespace ml
             KMeans(const KMeans&) = delete;
             KMeans& operator=(const KMeans&) = delete;
 
-            DLL_DECLSPEC bool fit(Eigen::Ref<const Eigen::MatrixXd> data) override;
+            DLL_DECLSPEC bool fit(DataView data) override;
 
-            unsigned int number_clusters() const override
-            {
-                return num_clusters_;
-            }
+            unsigned int number_clusters() const override { return number_clusters_; }
 
-            const std::vector<unsigned int>& labels() const override
-            {
-                return labels_;
-            }
+            const std::vector<unsigned int>& labels() const override { return labels_; }
 
-            const Eigen::MatrixXd& centroids() const override
-            {
-                return centroids_;
-            }
+            const Eigen::MatrixXd& centroids() const override { return centroids_; }
 
             DLL_DECLSPEC void set_seed(unsigned int seed);
 
@@ -56,52 +47,40 @@ namespace ml
             /** @throw std::invalid_argument If null. */
             DLL_DECLSPEC void set_centroids_initialiser(std::shared_ptr<const CentroidsInitialiser> centroids_initialiser);
 
-            void set_verbose(bool verbose)
-            {
-                verbose_ = verbose;
-            }
+            void set_verbose(bool verbose) { verbose_ = verbose; }
 
             /** Nearest centroid of x and the squared distance to it.
             @throw std::invalid_argument If x has the wrong size. */
-            DLL_DECLSPEC std::pair<unsigned int, double> assign_label(Eigen::Ref<const Eigen::VectorXd> x) const;
+            DLL_DECLSPEC std::pair<unsigned int, double> assign_label(PointView x) const;
 
             /** The same for every column of `points` (D x m) at once, on the device.
             @throw std::invalid_argument If `points` has the wrong number of rows.
             @throw std::logic_error If there is no fitted device state (no fit yet, or the N == K exact fit). */
-            DLL_DECLSPEC std::pair<std::vector<unsigned int>, std::vector<double>> assign_labels(Eigen::Ref<const Eigen::MatrixXd> points) const;
+            DLL_DECLSPEC std::pair<std::vector<unsigned int>, std::vector<double>> assign_labels(DataView points) const;
 
             /** Sum of squared distances of the points to their centroids. */
-            double inertia() const
-            {
-                return inertia_;
-            }
+            double inertia() const { return inertia_; }
 
-            bool converged() const override
-            {
-                return converged_;
-            }
+            bool converged() const override { return converged_; }
 
             /** Assignment steps executed by the last (single-initialisation) fit. */
-            unsigned int number_iterations() const
-            {
-                return number_iterations_;
-            }
+            unsigned int number_iterations() const { return number_iterations_; }
         private:
             std::vector<unsigned int> labels_;
             Eigen::MatrixXd centroids_;
-            std::default_random_engine prng_;
+            Prng prng_;
             std::shared_ptr<const CentroidsInitialiser> centroids_initialiser_;
             double absolute_tolerance_;
             double inertia_;
             unsigned int maximum_steps_;
-            unsigned int num_inits_;
-            unsigned int num_clusters_;
+            unsigned int number_initialisations_;
+            unsigned int number_clusters_;
             unsigned int number_iterations_;
             bool verbose_;
             bool converged_;
             mutable std::unique_ptr<detail::KmDevice> device_; /**< HBM-resident state of the last fit */
 
-            bool fit_once(Eigen::Ref<const Eigen::MatrixXd> data, detail::KmDevice& device);
+            bool fit_once(DataView data, detail::KmDevice& device);
         };
     }
 }

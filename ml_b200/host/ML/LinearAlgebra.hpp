@@ -3,6 +3,7 @@
 // device they are absorbed into the EM kernels; these versions serve EM::assign_responsibilities
 // and callers of the public API.
 #include <Eigen/Core>
+#include "Clustering.hpp"   // PointView
 #include "dll.hpp"
 
 namespace ml
@@ -11,13 +12,13 @@ namespace ml
 	{
 		/** x^T A x for symmetric A, reading only the upper triangle of A.
 		@throw std::invalid_argument If A is not square or x has the wrong size. */
-		DLL_DECLSPEC double xAx_symmetric(const Eigen::MatrixXd& A, Eigen::Ref<const Eigen::VectorXd> x);
+		DLL_DECLSPEC double xAx_symmetric(const Eigen::MatrixXd& A, PointView x);
 
 		/** dest = x x^T (dest is resized if needed). */
-		DLL_DECLSPEC void xxT(Eigen::Ref<const Eigen::VectorXd> x, Eigen::MatrixXd& dest);
+		DLL_DECLSPEC void xxT(PointView x, Eigen::MatrixXd& dest);
 
 		/** dest += a x x^T.
 		@throw std::invalid_argument If dest is not square or x has the wrong size. */
-		DLL_DECLSPEC void add_a_xxT(Eigen::Ref<const Eigen::VectorXd> x, Eigen::MatrixXd& dest, double a);
+		DLL_DECLSPEC void add_a_xxT(PointView x, Eigen::MatrixXd& dest, double a);
 	}
 }

@@ -148,75 +148,75 @@ namespace ml
 
 void init_clustering(py::module_& m)
 {
-	auto m_clustering = m.def_submodule("clustering", "Clustering algorithms.");
+	auto m_clustering = m.def_submodule("clustering", "Gaussian-mixture EM and K-means.");
 
 	py::class_<ml::Clustering::CentroidsInitialiser, std::shared_ptr<ml::Clustering::CentroidsInitialiser>>(m_clustering, "CentroidsInitialiser")
-		.doc() = "Abstract centroids initialiser.";
+		.doc() = "Base class of the strategies that pick K starting centroids.";
 
 	py::class_<ml::Clustering::ResponsibilitiesInitialiser, std::shared_ptr<ml::Clustering::ResponsibilitiesInitialiser>>(m_clustering, "ResponsibilitiesInitialiser")
-		.doc() = "Abstract responsibilities initialiser.";
+		.doc() = "Base class of the strategies that pick starting responsibilities (N x K).";
 
 	py::class_<ml::Clustering::Forgy, std::shared_ptr<ml::Clustering::Forgy>, ml::Clustering::CentroidsInitialiser>(m_clustering, "Forgy")
 		.def(py::init<>())
-		.doc() = "Forgy initialisation algorithm.";
+		.doc() = "K distinct data points, drawn without replacement, become the centroids.";
 
 	py::class_<ml::Clustering::RandomPartition, std::shared_ptr<ml::Clustering::RandomPartition>, ml::Clustering::CentroidsInitialiser>(m_clustering, "RandomPartition")
 		.def(py::init<>())
-		.doc() = "Random Partition initialisation algorithm.";
+		.doc() = "Every point joins one of K groups at random; the group means become the centroids.";
 
 	py::class_<ml::Clustering::KPP, std::shared_ptr<ml::Clustering::KPP>, ml::Clustering::CentroidsInitialiser>(m_clustering, "KPP")
 		.def(py::init<>())
-		.doc() = "KMeans++ initialisation algorithm.";
+		.doc() = "k-means++ seeding: each new centroid is a data point drawn with probability proportional to its squared distance from the centroids chosen so far (distance passes on the GPU).";
 
 	py::class_<ml::Clustering::ClosestCentroid, std::shared_ptr<ml::Clustering::ClosestCentroid>, ml::Clustering::ResponsibilitiesInitialiser>(m_clustering, "ClosestCentroid")
 		.def(py::init<std::shared_ptr<ml::Clustering::CentroidsInitialiser>>(), py::arg("centroids_initialiser"))
-		.doc() = "Initialises responsibilities by assigning every point to its closest initial centroid.";
+		.doc() = "One-hot responsibilities: each point belongs to the nearest of the centroids its centroids_initialiser picks.";
 
 	py::class_<ml::EMPy, std::shared_ptr<ml::EMPy>>(m_clustering, "EM")
-		.def(py::init<unsigned int>(), py::arg("number_components"), "Constructor.\n\nArgs:\n    number_components: Number of Gaussian components, > 0.")
-		.def("set_seed", &ml::EMPy::set_seed, py::arg("seed"), "Sets PRNG seed.")
-		.def("set_absolute_tolerance", &ml::EMPy::set_absolute_tolerance, py::arg("absolute_tolerance"), "Sets absolute tolerance.")
-		.def("set_relative_tolerance", &ml::EMPy::set_relative_tolerance, py::arg("relative_tolerance"), "Sets relative tolerance.")
-		.def("set_maximum_steps", &ml::EMPy::set_maximum_steps, py::arg("maximum_steps"), "Sets maximum number of iterations.")
-		.def("set_means_initialiser", &ml::EMPy::set_means_initialiser, py::arg("means_initialiser"), "Sets the algorithm to initialise component means.")
-		.def("set_responsibilities_initialiser", &ml::EMPy::set_responsibilities_initialiser, py::arg("responsibilities_initialiser"), "Sets the algorithm to initialise responsibilities.")
-		.def("set_verbose", &ml::EMPy::set_verbose, py::arg("verbose"), "Turns on/off the verbose mode.")
-		.def("set_maximise_first", &ml::EMPy::set_maximise_first, py::arg("maximise_first"), "Turns on/off doing an initial maximisation step before the E-M iterations.")
+		.def(py::init<unsigned int>(), py::arg("number_components"), "Args:\n    number_components: how many Gaussians the mixture has (at least 1).")
+		.def("set_seed", &ml::EMPy::set_seed, py::arg("seed"), "Seeds the pseudo-random generator the initialisers draw from.")
+		.def("set_absolute_tolerance", &ml::EMPy::set_absolute_tolerance, py::arg("absolute_tolerance"), "Absolute part of the stopping threshold (>= 0).")
+		.def("set_relative_tolerance", &ml::EMPy::set_relative_tolerance, py::arg("relative_tolerance"), "Relative part of the stopping threshold on the log-likelihood change (>= 0).")
+		.def("set_maximum_steps", &ml::EMPy::set_maximum_steps, py::arg("maximum_steps"), "Upper bound on the number of iterations (at least 2).")
+		.def("set_means_initialiser", &ml::EMPy::set_means_initialiser, py::arg("means_initialiser"), "Chooses how the starting means are picked.")
+		.def("set_responsibilities_initialiser", &ml::EMPy::set_responsibilities_initialiser, py::arg("responsibilities_initialiser"), "Chooses how the starting responsibilities are picked (used with set_maximise_first(True)).")
+		.def("set_verbose", &ml::EMPy::set_verbose, py::arg("verbose"), "Prints the state after every iteration when True.")
+		.def("set_maximise_first", &ml::EMPy::set_maximise_first, py::arg("maximise_first"), "When True the fit starts with an M-step on initial responsibilities instead of from initial means.")
 		.def("fit", &ml::EMPy::fit_row_major, py::arg("data").noconvert(),
-			"Fits the components to the data.\n\nArgs:\n    data: A 2D array with data points in rows.\n\nReturns:\n    True if EM algorithm converged.")
-		.def_property_readonly("number_components", &ml::EMPy::number_components, "Number of Gaussian components.")
-		.def_property_readonly("means", [](const ml::EMPy& em) { return to_numpy(em.means()); }, "Fitted means.")
-		.def_property_readonly("responsibilities", [](const ml::EMPy& em) { return to_numpy(em.responsibilities()); }, "Fitted responsibilities.")
-		.def_property_readonly("log_likelihood", &ml::EMPy::log_likelihood, "Maximised log-likelihood.")
-		.def_property_readonly("mixing_probabilities", [](const ml::EMPy& em) { return to_numpy(em.mixing_probabilities()); }, "Mixing probabilities of components.")
+			"Runs EM on the GPU.\n\nArgs:\n    data: float64 C-contiguous array of shape (N, D), one point per row; used as is, never converted.\n\nReturns:\n    Whether the log-likelihood change fell below the tolerance before maximum_steps.")
+		.def_property_readonly("number_components", &ml::EMPy::number_components, "K, as given to the constructor.")
+		.def_property_readonly("means", [](const ml::EMPy& em) { return to_numpy(em.means()); }, "Means after the fit, shape (D, K).")
+		.def_property_readonly("responsibilities", [](const ml::EMPy& em) { return to_numpy(em.responsibilities()); }, "Responsibilities of the last E-step, shape (N, K); brought to the host on first access.")
+		.def_property_readonly("log_likelihood", &ml::EMPy::log_likelihood, "Mean log-likelihood per point at the last E-step.")
+		.def_property_readonly("mixing_probabilities", [](const ml::EMPy& em) { return to_numpy(em.mixing_probabilities()); }, "Mixture weights, shape (K,).")
 		.def_property_readonly("number_iterations", &ml::EMPy::number_iterations, "Iterations run by the last fit.")
 		.def("covariance", [](const ml::EMPy& em, unsigned int k) { return to_numpy(em.covariance(k)); }, py::arg("k"),
-			"Returns k-th covariance matrix.\n\nArgs:\n    k: Component index.\n\nReturns:\n    2D square matrix.")
+			"Args:\n    k: component index in [0, K).\n\nReturns:\n    The (D, D) covariance of that component.")
 		.def("assign_responsibilities", &ml::EMPy::calculate_responsibilities, py::arg("x"),
-			"Given a data point x, calculate each component's responsibilities for x and return them.\n\nArgs:\n    x: Data point with correct number of dimensions.\n\nReturns:\n    1D array of responsibilities.")
+			"Args:\n    x: one point, D values.\n\nReturns:\n    The K responsibilities of the fitted components for x.")
 		.def("assign_responsibilities_batch", &ml::EMPy::calculate_responsibilities_batch, py::arg("data").noconvert(),
 			"Responsibilities of the fitted components for every row of data (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    2D array, one row of responsibilities per data point.")
-		.doc() = "Gaussian Expectation-Maximisation algorithm.";
+		.doc() = "Full-covariance Gaussian mixture fitted by expectation-maximisation on B200 GPUs.";
 
 	py::class_<ml::Clustering::KMeansPy, std::shared_ptr<ml::Clustering::KMeansPy>>(m_clustering, "KMeans")
-		.def(py::init<unsigned int>(), py::arg("number_clusters"), "Constructor.\n\nArgs:\n    number_clusters: Number of clusters, > 0.")
-		.def("set_seed", &ml::Clustering::KMeansPy::set_seed, py::arg("seed"), "Sets the PRNG seed.")
-		.def("set_absolute_tolerance", &ml::Clustering::KMeansPy::set_absolute_tolerance, py::arg("absolute_tolerance"), "Sets absolute tolerance.")
-		.def("set_maximum_steps", &ml::Clustering::KMeansPy::set_maximum_steps, py::arg("maximum_steps"), "Sets maximum number of iterations.")
-		.def("set_centroids_initialiser", &ml::Clustering::KMeansPy::set_centroids_initialiser, py::arg("centroids_initialiser"), "Sets the algorithm to initialise centroids.")
-		.def("set_number_initialisations", &ml::Clustering::KMeansPy::set_number_initialisations, py::arg("centroids_initialiser"), "Sets number of initialisations.")
-		.def("set_verbose", &ml::Clustering::KMeansPy::set_verbose, py::arg("verbose"), "Turns on/off the verbose mode.")
+		.def(py::init<unsigned int>(), py::arg("number_clusters"), "Args:\n    number_clusters: K, at least 1.")
+		.def("set_seed", &ml::Clustering::KMeansPy::set_seed, py::arg("seed"), "Seeds the pseudo-random generator the initialiser draws from.")
+		.def("set_absolute_tolerance", &ml::Clustering::KMeansPy::set_absolute_tolerance, py::arg("absolute_tolerance"), "Absolute part of the stopping threshold (>= 0).")
+		.def("set_maximum_steps", &ml::Clustering::KMeansPy::set_maximum_steps, py::arg("maximum_steps"), "Upper bound on the number of iterations (at least 2).")
+		.def("set_centroids_initialiser", &ml::Clustering::KMeansPy::set_centroids_initialiser, py::arg("centroids_initialiser"), "Chooses how the starting centroids are picked.")
+		.def("set_number_initialisations", &ml::Clustering::KMeansPy::set_number_initialisations, py::arg("centroids_initialiser"), "Number of independent starts; the converged one with the smallest inertia wins.")
+		.def("set_verbose", &ml::Clustering::KMeansPy::set_verbose, py::arg("verbose"), "Prints the state after every iteration when True.")
 		.def("fit", &ml::Clustering::KMeansPy::fit_row_major, py::arg("data").noconvert(),
-			"Fits the components to the data.\n\nArgs:\n    data: A 2D array with data points in rows.\n\nReturns:\n    True if K-means algorithm converged.")
-		.def_property_readonly("number_clusters", &ml::Clustering::KMeansPy::number_clusters, "Number of clusters.")
-		.def_property_readonly("centroids", &ml::Clustering::KMeansPy::centroids_row_major, "Fitted centroids.")
-		.def_property_readonly("labels", &ml::Clustering::KMeansPy::labels, "Fitted labels.")
-		.def_property_readonly("inertia", &ml::Clustering::KMeansPy::inertia, "Minimised inertia.")
+			"Runs Lloyd iterations on the GPU.\n\nArgs:\n    data: float64 C-contiguous array of shape (N, D), one point per row; used as is, never converted.\n\nReturns:\n    Whether the labels or the centroids stopped moving before maximum_steps.")
+		.def_property_readonly("number_clusters", &ml::Clustering::KMeansPy::number_clusters, "K, as given to the constructor.")
+		.def_property_readonly("centroids", &ml::Clustering::KMeansPy::centroids_row_major, "Centroids after the fit, shape (K, D).")
+		.def_property_readonly("labels", &ml::Clustering::KMeansPy::labels, "Cluster index of every fitted point.")
+		.def_property_readonly("inertia", &ml::Clustering::KMeansPy::inertia, "Sum of the squared distances of the points to their centroids.")
 		.def_property_readonly("converged", &ml::Clustering::KMeansPy::converged, "Whether the last fit converged.")
 		.def_property_readonly("number_iterations", &ml::Clustering::KMeansPy::number_iterations, "Assignment steps run by the last fit.")
 		.def("assign_label", &ml::Clustering::KMeansPy::assign_label_py, py::arg("x"),
-			"Given a data point x, assigns it to the closest cluster.\n\nArgs:\n    x: Data point with correct number of dimensions.\n\nReturns:\n    Tuple of cluster label and squared Euclidean distance to cluster centroid.")
+			"Args:\n    x: one point, D values.\n\nReturns:\n    (index of the nearest centroid, squared distance to it).")
 		.def("assign_labels", &ml::Clustering::KMeansPy::assign_labels_py, py::arg("data").noconvert(),
 			"Assigns every row of data to its closest cluster (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    Tuple of the array of cluster labels and the array of squared Euclidean distances to the cluster centroids.")
-		.doc() = "K-means clustering algorithm.";
+		.doc() = "Lloyd's K-means on B200 GPUs.";
 }

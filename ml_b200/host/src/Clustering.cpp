@@ -15,12 +15,12 @@ namespace ml
 	{
 		namespace
 		{
-			inline const double* point(Eigen::Ref<const Eigen::MatrixXd> data, Eigen::Index i)
+			inline const double* point(DataView data, Eigen::Index i)
 			{
 				return data.data() + i * data.outerStride();
 			}
 
-			inline double* column(Eigen::Ref<Eigen::MatrixXd> m, Eigen::Index j)
+			inline double* column(MatrixOut m, Eigen::Index j)
 			{
 				return m.data() + j * m.outerStride();
 			}
@@ -42,7 +42,7 @@ namespace ml
 
 		ResponsibilitiesInitialiser::~ResponsibilitiesInitialiser() = default;
 
-		void Forgy::init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, const unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids) const
+		void Forgy::init(DataView data, Prng& prng, const unsigned int number_components, MatrixOut centroids) const
 		{
 			// std::sample over 0..N-1 (selection sampling): the draw sequence the reference makes.
 			std::vector<Eigen::Index> population(static_cast<size_t>(data.cols()));
@@ -55,7 +55,7 @@ namespace ml
 			}
 		}
 
-		void RandomPartition::init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, const unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids) const
+		void RandomPartition::init(DataView data, Prng& prng, const unsigned int number_components, MatrixOut centroids) const
 		{
 			const Eigen::Index dim = data.rows();
 			for (unsigned int k = 0; k < number_components; ++k) {
@@ -74,7 +74,7 @@ namespace ml
 			}
 		}
 
-		void KPP::init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, const unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> centroids) const
+		void KPP::init(DataView data, Prng& prng, const unsigned int number_components, MatrixOut centroids) const
 		{
 			// Weight of a point = squared distance to the nearest centroid chosen so far (1 for the
 			// first draw).  The minimum is kept incrementally: one pass over the data per new centroid,
@@ -105,7 +105,7 @@ namespace ml
 			}
 		}
 
-		void ClosestCentroid::init(Eigen::Ref<const Eigen::MatrixXd> data, std::default_random_engine& prng, unsigned int number_components, Eigen::Ref<Eigen::MatrixXd> responsibilities) const
+		void ClosestCentroid::init(DataView data, Prng& prng, unsigned int number_components, MatrixOut responsibilities) const
 		{
 			const Eigen::Index dim = data.rows();
 			Eigen::MatrixXd centroids(dim, number_components);

@@ -104,7 +104,7 @@ namespace ml
 		return responsibilities_;
 	}
 
-	bool EM::fit(const Eigen::Ref<const Eigen::MatrixXd> data)
+	bool EM::fit(const DataView data)
 	{
 		converged_ = false;
 		number_iterations_ = 0;
@@ -216,7 +216,7 @@ namespace ml
 		return converged_;
 	}
 
-	void EM::initialise_centroids(const Clustering::CentroidsInitialiser& initialiser, Eigen::Ref<const Eigen::MatrixXd> data, Eigen::Ref<Eigen::MatrixXd> centroids)
+	void EM::initialise_centroids(const Clustering::CentroidsInitialiser& initialiser, DataView data, MatrixOut centroids)
 	{
 		if (typeid(initialiser) == typeid(Clustering::KPP)) {
 			// the built-in K-means++: distance passes on the device, draws here (Clustering.cpp:39-59)
@@ -284,7 +284,7 @@ namespace ml
 		}
 	}
 
-	Eigen::MatrixXd EM::assign_responsibilities(Eigen::Ref<const Eigen::MatrixXd> points) const
+	Eigen::MatrixXd EM::assign_responsibilities(DataView points) const
 	{
 		if (points.rows() != means().rows()) {
 			throw std::invalid_argument("Wrong number of rows");
@@ -297,7 +297,7 @@ namespace ml
 		return result;
 	}
 
-	void EM::assign_responsibilities(Eigen::Ref<const Eigen::VectorXd> x, Eigen::Ref<Eigen::VectorXd> u) const
+	void EM::assign_responsibilities(PointView x, VectorOut u) const
 	{
 		if (x.size() != means().rows()) {
 			throw std::invalid_argument("Wrong x size");

@@ -20,8 +20,8 @@ namespace ml
 			, absolute_tolerance_(1e-8)
 			, inertia_(0)
 			, maximum_steps_(1000)
-			, num_inits_(1)
-			, num_clusters_(number_clusters)
+			, number_initialisations_(1)
+			, number_clusters_(number_clusters)
 			, number_iterations_(0)
 			, verbose_(false)
 			, converged_(false)
@@ -33,23 +33,23 @@ namespace ml
 
 		KMeans::~KMeans() = default;
 
-		bool KMeans::fit(Eigen::Ref<const Eigen::MatrixXd> data)
+		bool KMeans::fit(DataView data)
 		{
 			const auto number_dimensions = static_cast<unsigned int>(data.rows());
 			const auto sample_size = static_cast<unsigned int>(data.cols());
 			if (!number_dimensions) {
 				throw std::invalid_argument("KMeans: At least one dimension required");
 			}
-			if (sample_size < num_clusters_) {
+			if (sample_size < number_clusters_) {
 				throw std::invalid_argument("KMeans: Not enough data ");
 			}
 			converged_ = false;
 			number_iterations_ = 0;
 			device_.reset();
-			centroids_.resize(number_dimensions, num_clusters_);
+			centroids_.resize(number_dimensions, number_clusters_);
 			labels_.resize(sample_size);
 
-			if (sample_size == num_clusters_) {
+			if (sample_size == number_clusters_) {
 				// Every point is its own cluster (KMeans.cpp:67-75); identical for every initialisation.
 				for (unsigned int i = 0; i < sample_size; ++i) {
 					std::copy_n(data.data() + static_cast<Eigen::Index>(i) * data.outerStride(), number_dimensions, centroids_.data() + static_cast<Eigen::Index>(i) * number_dimensions);
@@ -60,16 +60,16 @@ namespace ml
 				return converged_;
 			}
 
-			device_ = std::make_unique<detail::KmDevice>(data, num_clusters_);
+			device_ = std::make_unique<detail::KmDevice>(data, number_clusters_);
 			detail::KmDevice& device = *device_;
-			if (num_inits_ == 1) {
+			if (number_initialisations_ == 1) {
 				fit_once(data, device);
 			} else {
-				// Best of num_inits_ runs by inertia (KMeans.cpp:29-47).
+				// Best of number_initialisations_ runs by inertia (KMeans.cpp:29-47).
 				double min_inertia = std::numeric_limits<double>::infinity();
 				Eigen::MatrixXd best_centroids;
 				bool any_converged = false;
-				for (unsigned int i = 0; i < num_inits_; ++i) {
+				for (unsigned int i = 0; i < number_initialisations_; ++i) {
 					if (fit_once(data, device)) {
 						if (inertia_ < min_inertia) {
 							min_inertia = inertia_;
@@ -90,15 +90,15 @@ namespace ml
 			return converged_;
 		}
 
-		bool KMeans::fit_once(Eigen::Ref<const Eigen::MatrixXd> data, detail::KmDevice& device)
+		bool KMeans::fit_once(DataView data, detail::KmDevice& device)
 		{
 			converged_ = false;
 			const CentroidsInitialiser& initialiser = *centroids_initialiser_;
 			if (typeid(initialiser) == typeid(KPP)) {
 				// the built-in K-means++: distance passes on the device, draws here (Clustering.cpp:39-59)
-				detail::kpp_on_device(*device.data(), data, prng_, num_clusters_, centroids_);
+				detail::kpp_on_device(*device.data(), data, prng_, number_clusters_, centroids_);
 			} else {
-				initialiser.init(data, prng_, num_clusters_, centroids_);
+				initialiser.init(data, prng_, number_clusters_, centroids_);
 			}
 			device.set_centroids(centroids_);
 			for (unsigned int step = 0; step < maximum_steps_; ++step) {
@@ -114,7 +114,7 @@ namespace ml
 				if (verbose_) {
 					device.get_centroids(centroids_);
 					std::cout << "Step " << step << "\n";
-					for (unsigned int k = 0; k < num_clusters_; ++k) {
+					for (unsigned int k = 0; k < number_clusters_; ++k) {
 						std::cout << "Centroid[" << k << "] ==";
 						for (Eigen::Index l = 0; l < centroids_.rows(); ++l) {
 							std::cout << " " << centroids_(l, k);
@@ -159,7 +159,7 @@ namespace ml
 			if (number_initialisations < 1) {
 				throw std::invalid_argument("KMeans: At least 1 initialisation required");
 			}
-			num_inits_ = number_initialisations;
+			number_initialisations_ = number_initialisations;
 		}
 
 		void KMeans::set_centroids_initialiser(std::shared_ptr<const CentroidsInitialiser> centroids_initialiser)
@@ -170,7 +170,7 @@ namespace ml
 			centroids_initialiser_ = centroids_initialiser;
 		}
 
-		std::pair<std::vector<unsigned int>, std::vector<double>> KMeans::assign_labels(Eigen::Ref<const Eigen::MatrixXd> points) const
+		std::pair<std::vector<unsigned int>, std::vector<double>> KMeans::assign_labels(DataView points) const
 		{
 			if (points.rows() != centroids_.rows()) {
 				throw std::invalid_argument("KMeans: wrong number of rows");
@@ -183,7 +183,7 @@ namespace ml
 			return result;
 		}
 
-		std::pair<unsigned int, double> KMeans::assign_label(Eigen::Ref<const Eigen::VectorXd> x) const
+		std::pair<unsigned int, double> KMeans::assign_label(PointView x) const
 		{
 			if (x.size() != centroids_.rows()) {
 				throw std::invalid_argument("KMeans: wrong size of x");
@@ -191,7 +191,7 @@ namespace ml
 			const Eigen::Index dim = centroids_.rows();
 			unsigned int label = 0;
 			double smallest = std::numeric_limits<double>::infinity();
-			for (unsigned int k = 0; k < num_clusters_; ++k) {
+			for (unsigned int k = 0; k < number_clusters_; ++k) {
 				const double* c = centroids_.data() + static_cast<Eigen::Index>(k) * dim;
 				double distance = 0;
 				for (Eigen::Index l = 0; l < dim; ++l) {

@@ -8,7 +8,7 @@ namespace ml
 {
 	namespace LinearAlgebra
 	{
-		double xAx_symmetric(const Eigen::MatrixXd& A, Eigen::Ref<const Eigen::VectorXd> x)
+		double xAx_symmetric(const Eigen::MatrixXd& A, PointView x)
 		{
 			const Eigen::Index n = A.rows();
 			if (A.cols() != n) {
@@ -31,7 +31,7 @@ namespace ml
 			return total;
 		}
 
-		void xxT(Eigen::Ref<const Eigen::VectorXd> x, Eigen::MatrixXd& dest)
+		void xxT(PointView x, Eigen::MatrixXd& dest)
 		{
 			const Eigen::Index n = x.size();
 			if (dest.rows() != n || dest.cols() != n) {
@@ -49,7 +49,7 @@ namespace ml
 			}
 		}
 
-		void add_a_xxT(Eigen::Ref<const Eigen::VectorXd> x, Eigen::MatrixXd& dest, const double a)
+		void add_a_xxT(PointView x, Eigen::MatrixXd& dest, const double a)
 		{
 			const Eigen::Index n = dest.rows();
 			if (dest.cols() != n) {
