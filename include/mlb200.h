@@ -58,6 +58,11 @@ int mlb_device_count(int* count);      /* cudaGetDeviceCount */
  * values on device 0, so that tests can bound its error against libm.  Replaces std::exp of EM.cpp:206. */
 int mlb_selftest_exp(const double* x, int64_t n, double* out);
 
+/* Diagnostic: the FP64 peaks of `device` in TFLOP/s, measured now with two dependent-chain micro-kernels that saturate
+ * the SM's FP64 unit: mma.sync.m8n8k4.f64 (DMMA, the instruction the kernels issue) and DFMA.  About 50 ms.  bench.py
+ * uses the DMMA figure as its roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+int mlb_selftest_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
+
 /* ---------------------------------------------------------------- context */
 
 /* One process driving n_devices local GPUs (n_devices in {1,2,4,8}); devices == NULL means
@@ -72,6 +77,11 @@ int mlb_ctx_create_rank(int device, int rank, int world, const void* nccl_unique
 
 int mlb_ctx_destroy(mlb_ctx* ctx);
 int mlb_ctx_world(const mlb_ctx* ctx, int* world, int* n_local, int* first_rank);
+
+/* Sum of `local` over the ranks of a one-process-per-GPU job (one 8-byte ncclAllGather; every rank must call it);
+ * in a single-process context *total = local.  The host classes use it to learn the total point count when every
+ * rank passes its own rows to fit(). */
+int mlb_ctx_sum_int64(mlb_ctx* ctx, int64_t local, int64_t* total);
 
 /* Blocks until every local stream of the context is idle. */
 int mlb_ctx_synchronize(mlb_ctx* ctx);

@@ -31,11 +31,13 @@ SIGNATURES = {
     "mlb_last_error": (ctypes.c_char_p, []),
     "mlb_device_count": (ctypes.c_int, [_c_ip]),
     "mlb_selftest_exp": (ctypes.c_int, [_vp, ctypes.c_int64, _vp]),
+    "mlb_selftest_fp64_peak": (ctypes.c_int, [ctypes.c_int, _c_dp, _c_dp]),
     "mlb_ctx_create": (ctypes.c_int, [_c_ip, ctypes.c_int, ctypes.POINTER(_vp)]),
     "mlb_nccl_unique_id": (ctypes.c_int, [_vp]),
     "mlb_ctx_create_rank": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp, ctypes.POINTER(_vp)]),
     "mlb_ctx_destroy": (ctypes.c_int, [_vp]),
     "mlb_ctx_world": (ctypes.c_int, [_vp, _c_ip, _c_ip, _c_ip]),
+    "mlb_ctx_sum_int64": (ctypes.c_int, [_vp, ctypes.c_int64, _c_i64p]),
     "mlb_ctx_synchronize": (ctypes.c_int, [_vp]),
     "mlb_ctx_timer_start": (ctypes.c_int, [_vp]),
     "mlb_ctx_timer_stop": (ctypes.c_int, [_vp, _c_dp]),
@@ -124,6 +126,13 @@ def selftest_exp(x):
     out = np.empty_like(x)
     check(lib().mlb_selftest_exp(x.ctypes.data, x.size, out.ctypes.data))
     return out
+
+
+def fp64_peak(device=0):
+    """(DMMA, DFMA) TFLOP/s of `device`, measured now (diagnostic; bench.py's roofline denominator)."""
+    a, b = ctypes.c_double(), ctypes.c_double()
+    check(lib().mlb_selftest_fp64_peak(device, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
 
 
 def shard_range(n_total, world, rank):

@@ -87,15 +87,16 @@ static bool is_pinned_host(const void* ptr)
     return attr.type == cudaMemoryTypeHost;
 }
 
+// Processes of a one-process-per-GPU job share the host's cores: every rank takes its share of the copy threads.
+static int g_ranks_on_host = 1;
+
 static int copy_threads(size_t bytes)
 {
     if (bytes < kThreadedCopyBytes) return 1;
-    static const int configured = [] {
-        int t = static_cast<int>(std::min<unsigned>(kCopyThreadsMax, std::max(1u, std::thread::hardware_concurrency() / 2)));
-        if (const char* env = std::getenv("MLB200_COPY_THREADS")) t = std::max(1, std::min(kCopyThreadsMax, std::atoi(env)));
-        return t;
-    }();
-    return configured;
+    const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+    int t = static_cast<int>(std::min<unsigned>(kCopyThreadsMax, std::max(2u, cores / (2u * static_cast<unsigned>(g_ranks_on_host)))));
+    if (const char* env = std::getenv("MLB200_COPY_THREADS")) t = std::max(1, std::min(kCopyThreadsMax, std::atoi(env)));
+    return t;
 }
 
 // Runs body(t) on `threads` host threads (the caller is thread 0) and returns the first failure.
@@ -336,10 +337,23 @@ __global__ void reduce_groups_kernel(const double* __restrict__ partials, Vshard
     }
 }
 
-int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s)
+void ReduceScratch::release(mlb_ctx* ctx)
+{
+    for (size_t g = 0; g < ptr.size(); ++g)
+        if (ptr[g]) {
+            cudaSetDevice(ctx->gpus[g].device);
+            cudaFreeAsync(ptr[g], ctx->gpus[g].stream);
+        }
+    ptr.clear();
+    len.clear();
+}
+
+int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s, ReduceScratch& scratch)
 {
     mlb_ctx* ctx = data->ctx;
     const int vpg = ctx->vshards_per_gpu();
+    scratch.ptr.resize(ctx->gpus.size(), nullptr);
+    scratch.len.resize(ctx->gpus.size(), 0);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
         VshardRanges r, rg;
@@ -360,19 +374,18 @@ int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, co
             return MLB_OK;
         }
         const size_t need = static_cast<size_t>(total_groups) * s;
-        if (sh.reduce_scratch_len < need) {
-            if (sh.reduce_scratch) {
-                MLB_CUDA(cudaStreamSynchronize(gpu.stream));
-                MLB_CUDA(cudaFreeAsync(sh.reduce_scratch, gpu.stream));
-                sh.reduce_scratch = nullptr;
-                sh.reduce_scratch_len = 0;
+        if (scratch.len[g] < need) {
+            if (scratch.ptr[g]) {
+                MLB_CUDA(cudaFreeAsync(scratch.ptr[g], gpu.stream));   // stream-ordered: earlier readers are done first
+                scratch.ptr[g] = nullptr;
+                scratch.len[g] = 0;
             }
-            MLB_CUDA(cudaMallocAsync(&sh.reduce_scratch, sizeof(double) * need, gpu.stream));
-            sh.reduce_scratch_len = need;
+            MLB_CUDA(cudaMallocFromPoolAsync(&scratch.ptr[g], sizeof(double) * need, gpu.pool, gpu.stream));
+            scratch.len[g] = need;
         }
-        reduce_groups_kernel<<<dim3((s + 31) / 32, static_cast<unsigned>(total_groups)), dim3(32, 8), 0, gpu.stream>>>(partials[g], r, vpg, s, sh.reduce_scratch);
+        reduce_groups_kernel<<<dim3((s + 31) / 32, static_cast<unsigned>(total_groups)), dim3(32, 8), 0, gpu.stream>>>(partials[g], r, vpg, s, scratch.ptr[g]);
         MLB_CUDA(cudaGetLastError());
-        reduce_partials_kernel<<<dim3((s + 31) / 32, vpg), dim3(32, 8), 0, gpu.stream>>>(sh.reduce_scratch, rg, s, out);
+        reduce_partials_kernel<<<dim3((s + 31) / 32, vpg), dim3(32, 8), 0, gpu.stream>>>(scratch.ptr[g], rg, s, out);
         MLB_CUDA(cudaGetLastError());
         return MLB_OK;
     }));
@@ -422,8 +435,8 @@ static int compute_shift(mlb_data* data)
     std::vector<double*> partials(ctx->gpus.size(), nullptr), vsum(ctx->gpus.size(), nullptr);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMallocAsync(&partials[g], sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * d, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&vsum[g], sizeof(double) * kVirtualShards * d, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&partials[g], sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * d, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&vsum[g], sizeof(double) * kVirtualShards * d, gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(vsum[g], 0, sizeof(double) * kVirtualShards * d, gpu.stream));
         if (sh.n_chunks() > 0) {
             const int threads = std::max(d, 256 / d * d);
@@ -433,7 +446,10 @@ static int compute_shift(mlb_data* data)
         }
         return MLB_OK;
     }));
-    MLB_TRY(reduce_and_exchange(data, partials, vsum, d));
+    ReduceScratch scratch;
+    const int rc_reduce = reduce_and_exchange(data, partials, vsum, d, scratch);
+    scratch.release(ctx);
+    MLB_TRY(rc_reduce);
     std::vector<double> host(static_cast<size_t>(kVirtualShards) * d);
     MLB_CUDA(cudaSetDevice(ctx->gpus[0].device));
     MLB_CUDA(cudaMemcpyAsync(host.data(), vsum[0], sizeof(double) * host.size(), cudaMemcpyDeviceToHost, ctx->gpus[0].stream));
@@ -442,7 +458,7 @@ static int compute_shift(mlb_data* data)
     for (int c = 0; c < d; ++c) data->shift[c] = tree8(host.data() + c, d) / static_cast<double>(data->lay.n_total);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMallocAsync(&sh.shift, sizeof(double) * d, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&sh.shift, sizeof(double) * d, gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(sh.shift, data->shift.data(), sizeof(double) * d, cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
         MLB_CUDA(cudaFreeAsync(partials[g], gpu.stream));
@@ -545,13 +561,18 @@ static int init_gpu(Gpu& gpu)
 {
     MLB_CUDA(cudaSetDevice(gpu.device));
     MLB_CUDA(cudaStreamCreateWithFlags(&gpu.stream, cudaStreamNonBlocking));
-    // All device buffers are stream-ordered allocations from the device's default pool, which keeps freed memory
-    // cached: a second fit reuses the first one's buffers instead of paying cudaMalloc / cudaFree (milliseconds each
-    // at these sizes).  The cache is returned to the driver when the context is destroyed.
-    cudaMemPool_t pool = nullptr;
-    MLB_CUDA(cudaDeviceGetDefaultMemPool(&pool, gpu.device));
+    // All device buffers are stream-ordered allocations from a pool the context owns (never the device's default
+    // pool, which other CUDA code in the process, e.g. PyTorch, may be using with its own settings).  The pool keeps
+    // freed memory cached: a second fit reuses the first one's buffers instead of paying cudaMalloc / cudaFree
+    // (milliseconds each at these sizes).  The pool is destroyed with the context.
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = gpu.device;
+    MLB_CUDA(cudaMemPoolCreate(&gpu.pool, &props));
     uint64_t keep = UINT64_MAX;
-    MLB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    MLB_CUDA(cudaMemPoolSetAttribute(gpu.pool, cudaMemPoolAttrReleaseThreshold, &keep));
     MLB_CUDA(cudaEventCreate(&gpu.ev0));
     MLB_CUDA(cudaEventCreate(&gpu.ev1));
     return MLB_OK;
@@ -623,6 +644,7 @@ int mlb_ctx_create_rank(int device, int rank, int world, const void* nccl_unique
     auto* ctx = new mlb_ctx;
     ctx->world = world;
     ctx->rank_mode = true;
+    g_ranks_on_host = world;
     ctx->gpus.resize(1);
     ctx->gpus[0].device = device;
     ctx->gpus[0].rank = rank;
@@ -658,8 +680,7 @@ int mlb_ctx_destroy(mlb_ctx* ctx)
             if (gpu.bounce_ev[i]) cudaEventDestroy(gpu.bounce_ev[i]);
         }
         if (gpu.stream) cudaStreamDestroy(gpu.stream);
-        cudaMemPool_t pool = nullptr;
-        if (cudaDeviceGetDefaultMemPool(&pool, gpu.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        if (gpu.pool) cudaMemPoolDestroy(gpu.pool);
     }
     delete ctx;
     return MLB_OK;
@@ -676,6 +697,7 @@ int mlb_ctx_world(const mlb_ctx* ctx, int* world, int* n_local, int* first_rank)
 
 int mlb_ctx_synchronize(mlb_ctx* ctx)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx, "mlb_ctx_synchronize: null context");
     return for_each_gpu(ctx, [&](int, Gpu& gpu) -> int {
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
@@ -683,8 +705,40 @@ int mlb_ctx_synchronize(mlb_ctx* ctx)
     });
 }
 
+int mlb_ctx_sum_int64(mlb_ctx* ctx, int64_t local, int64_t* total)
+{
+    MLB_ENTER(ctx);
+    MLB_REQUIRE(ctx && total, "mlb_ctx_sum_int64: null argument");
+    if (!ctx->rank_mode || ctx->world == 1) {
+        *total = local;
+        return MLB_OK;
+    }
+    Gpu& gpu = ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    MLB_NCCL_API(api);
+    int64_t* dev = nullptr;
+    MLB_CUDA(cudaMallocFromPoolAsync(&dev, sizeof(int64_t) * ctx->world, gpu.pool, gpu.stream));
+    std::vector<int64_t> host(static_cast<size_t>(ctx->world), 0);
+    int rc = MLB_OK;
+    auto body = [&]() -> int {
+        MLB_CUDA(cudaMemcpyAsync(dev + gpu.rank, &local, sizeof(int64_t), cudaMemcpyHostToDevice, gpu.stream));
+        MLB_NCCL(api, api->AllGather(dev + gpu.rank, dev, 1, ncclInt64, gpu.comm, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(host.data(), dev, sizeof(int64_t) * ctx->world, cudaMemcpyDeviceToHost, gpu.stream));
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    };
+    rc = body();
+    cudaFreeAsync(dev, gpu.stream);
+    MLB_TRY(rc);
+    int64_t sum = 0;
+    for (int64_t v : host) sum += v;
+    *total = sum;
+    return MLB_OK;
+}
+
 int mlb_ctx_timer_start(mlb_ctx* ctx)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx, "mlb_ctx_timer_start: null context");
     return for_each_gpu(ctx, [&](int, Gpu& gpu) -> int {
         MLB_CUDA(cudaEventRecord(gpu.ev0, gpu.stream));
@@ -694,6 +748,7 @@ int mlb_ctx_timer_start(mlb_ctx* ctx)
 
 int mlb_ctx_timer_stop(mlb_ctx* ctx, double* elapsed_ms)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx && elapsed_ms, "mlb_ctx_timer_stop: null argument");
     MLB_TRY(for_each_gpu(ctx, [&](int, Gpu& gpu) -> int {
         MLB_CUDA(cudaEventRecord(gpu.ev1, gpu.stream));
@@ -745,13 +800,13 @@ static int make_shards(mlb_ctx* ctx, int64_t n_total, int d, mlb_data** out)
 
 int mlb_data_free(mlb_data* data)
 {
+    MLB_ENTER(data ? data->ctx : nullptr);
     if (!data) return MLB_OK;
     for (size_t g = 0; g < data->shards.size(); ++g) {
         cudaSetDevice(data->ctx->gpus[g].device);
         cudaStreamSynchronize(data->ctx->gpus[g].stream);
         if (data->shards[g].owned && data->shards[g].x) cudaFreeAsync(data->shards[g].x, data->ctx->gpus[g].stream);
         if (data->shards[g].shift) cudaFreeAsync(data->shards[g].shift, data->ctx->gpus[g].stream);
-        if (data->shards[g].reduce_scratch) cudaFreeAsync(data->shards[g].reduce_scratch, data->ctx->gpus[g].stream);
         if (data->shards[g].nearest) cudaFreeAsync(data->shards[g].nearest, data->ctx->gpus[g].stream);
         if (data->shards[g].seed_centroid) cudaFreeAsync(data->shards[g].seed_centroid, data->ctx->gpus[g].stream);
     }
@@ -761,6 +816,7 @@ int mlb_data_free(mlb_data* data)
 
 int mlb_data_upload(mlb_ctx* ctx, const double* x, int64_t n, int64_t n_total, int d, int64_t ld, mlb_data** out)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx && x && out, "mlb_data_upload: null argument");
     MLB_REQUIRE(d >= 1, "mlb_data_upload: at least one dimension required");
     MLB_REQUIRE(ld >= d, "mlb_data_upload: outer stride %lld smaller than d=%d", static_cast<long long>(ld), d);
@@ -776,7 +832,7 @@ int mlb_data_upload(mlb_ctx* ctx, const double* x, int64_t n, int64_t n_total, i
     }
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMallocAsync(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d, gpu.pool, gpu.stream));
         if (sh.n() > 0) {
             const double* src = x + (sh.begin - host_begin) * ld;
             MLB_TRY(staged_h2d(gpu, sh.x, src, static_cast<size_t>(sh.n()), sizeof(double) * d, sizeof(double) * ld));
@@ -794,6 +850,7 @@ int mlb_data_upload(mlb_ctx* ctx, const double* x, int64_t n, int64_t n_total, i
 
 int mlb_data_wrap_device(mlb_ctx* ctx, const double* x_device, int64_t n, int d, mlb_data** out)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx && x_device && out, "mlb_data_wrap_device: null argument");
     MLB_REQUIRE(ctx->world == 1, "mlb_data_wrap_device: 1-GPU contexts only");
     MLB_REQUIRE(d >= 1 && n >= 1 && n < (1ll << 32), "mlb_data_wrap_device: bad shape");
@@ -813,6 +870,7 @@ int mlb_data_wrap_device(mlb_ctx* ctx, const double* x_device, int64_t n, int d,
 int mlb_data_generate_gmm(mlb_ctx* ctx, int64_t n_total, int d, int k_true, uint64_t seed, double spread,
                           double* true_means, mlb_data** out)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx && out, "mlb_data_generate_gmm: null argument");
     MLB_REQUIRE(d >= 1 && d <= kMaxGenDim && k_true >= 1 && n_total >= 1 && n_total < (1ll << 32), "mlb_data_generate_gmm: bad shape");
     // Mixture parameters: a pure function of (seed, d, k_true), drawn on the host.
@@ -866,11 +924,11 @@ int mlb_data_generate_gmm(mlb_ctx* ctx, int64_t n_total, int d, int k_true, uint
     MLB_TRY(make_shards(ctx, n_total, d, &data));
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMallocAsync(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&sh.x, sizeof(double) * std::max<int64_t>(1, sh.n()) * d, gpu.pool, gpu.stream));
         double *dm = nullptr, *dl = nullptr, *dw = nullptr;
-        MLB_CUDA(cudaMallocAsync(&dm, sizeof(double) * means.size(), gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&dl, sizeof(double) * chol.size(), gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&dw, sizeof(double) * cum.size(), gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dm, sizeof(double) * means.size(), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dl, sizeof(double) * chol.size(), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dw, sizeof(double) * cum.size(), gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(dm, means.data(), sizeof(double) * means.size(), cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(dl, chol.data(), sizeof(double) * chol.size(), cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(dw, cum.data(), sizeof(double) * cum.size(), cudaMemcpyHostToDevice, gpu.stream));
@@ -896,6 +954,7 @@ int mlb_data_generate_gmm(mlb_ctx* ctx, int64_t n_total, int d, int k_true, uint
 
 int mlb_data_download(mlb_data* data, int64_t begin, int64_t count, double* out)
 {
+    MLB_ENTER(data ? data->ctx : nullptr);
     MLB_REQUIRE(data && out, "mlb_data_download: null argument");
     MLB_REQUIRE(begin >= 0 && count >= 0 && begin + count <= data->lay.n_total, "mlb_data_download: range out of bounds");
     const int d = data->d;

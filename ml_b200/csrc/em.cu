@@ -612,6 +612,7 @@ struct mlb_em {
     cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
     int64_t launches_per_step = 0;
     int plain_steps = 0;         // steps launched the ordinary way since creation (the first two size the scratch buffers)
+    ReduceScratch reduce_scratch;   // owned here: the captured step graph has its address baked in
 
     double* means(int g) const { return gpus[g].params; }
     double* covs(int g) const { return gpus[g].params + d * k; }
@@ -760,7 +761,7 @@ static int enqueue_step_plain(mlb_em* em)
     }));
     std::vector<double*> partials, vsum;
     for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
-    MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV));
+    MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV, em->reduce_scratch));
     em->launches += static_cast<int64_t>(ctx->gpus.size());
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
         return launch_finalize(em, g, true, em->cur ^ 1, true);
@@ -830,13 +831,15 @@ static int mstep_from_device(mlb_em* em, std::vector<double*>& dev, int rc)
         if (rc == MLB_OK) {
             std::vector<double*> partials, vsum;
             for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
-            rc = reduce_and_exchange(em->data, partials, vsum, em->SV);
+            rc = reduce_and_exchange(em->data, partials, vsum, em->SV, em->reduce_scratch);
             em->launches += static_cast<int64_t>(ctx->gpus.size());
         }
         if (rc == MLB_OK)
             rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, true, em->cur, false); });
-        if (rc == MLB_OK) rc = mlb_ctx_synchronize(ctx);
     }
+    // on every path: a pinned source of staged_h2d is still being read by the DMA engine until the stream is idle
+    const int rc_sync = mlb_ctx_synchronize(ctx);
+    if (rc == MLB_OK) rc = rc_sync;
     for (size_t g = 0; g < dev.size(); ++g)
         if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(dev[g], ctx->gpus[g].stream); }
     if (rc == MLB_OK) { em->have_params = true; em->have_step = false; }
@@ -875,6 +878,7 @@ int mlb_selftest_exp(const double* x, int64_t n, double* out)
 
 int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx && data && out, "mlb_em_create: null argument");
     MLB_REQUIRE(data->ctx == ctx, "mlb_em_create: data belongs to another context");
     MLB_REQUIRE(k >= 1, "mlb_em_create: number of components must be positive");
@@ -960,22 +964,22 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         EmGpu& eg = em->gpus[g];
         const DataShard& sh = data->shards[g];
         const size_t theta_len = static_cast<size_t>(em_theta_len(DP, KP));
-        MLB_CUDA(cudaMallocAsync(&eg.theta[0], sizeof(double) * theta_len, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.theta[1], sizeof(double) * theta_len, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.params, sizeof(double) * em->params_len(), gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.vsum, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.ll, sizeof(double) * kLlRing, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.ll_counter, sizeof(unsigned long long), gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.theta[0], sizeof(double) * theta_len, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.theta[1], sizeof(double) * theta_len, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.params, sizeof(double) * em->params_len(), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.vsum, sizeof(double) * kVirtualShards * em->SV, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.ll, sizeof(double) * kLlRing, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.ll_counter, sizeof(unsigned long long), gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(eg.ll_counter, 0, sizeof(unsigned long long), gpu.stream));
         {
             const size_t fin_smem = sizeof(double) * (3 * em->d * em->d + 3 * em->d);
             if (fin_smem > 48 * 1024)
                 MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em_finalize_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)));
         }
-        MLB_CUDA(cudaMallocAsync(&eg.feat_m, sizeof(int2) * em->feat_m.size(), gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.feat_e, sizeof(int2) * em->feat_e.size(), gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&eg.counter, sizeof(unsigned), gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_m, sizeof(int2) * em->feat_m.size(), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_e, sizeof(int2) * em->feat_e.size(), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.counter, sizeof(unsigned), gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(eg.vsum, 0, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(eg.feat_m, em->feat_m.data(), sizeof(int2) * em->feat_m.size(), cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(eg.feat_e, em->feat_e.data(), sizeof(int2) * em->feat_e.size(), cudaMemcpyHostToDevice, gpu.stream));
@@ -992,13 +996,13 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         } else {
             std::vector<int2> off(em->feat_e.size());
             for (size_t i = 0; i < off.size(); ++i) off[i] = em->feat_e[i].x < 0 ? make_int2(DP + 1, DP + 1) : em->feat_e[i];
-            MLB_CUDA(cudaMallocAsync(&eg.feat_e_off, sizeof(int2) * off.size(), gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_e_off, sizeof(int2) * off.size(), gpu.pool, gpu.stream));
             MLB_CUDA(cudaMemcpyAsync(eg.feat_e_off, off.data(), sizeof(int2) * off.size(), cudaMemcpyHostToDevice, gpu.stream));
             MLB_CUDA(cudaStreamSynchronize(gpu.stream));   // `off` is a local
-            MLB_CUDA(cudaMallocAsync(&eg.r, sizeof(double) * std::max<int64_t>(1, sh.n()) * KP, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.r, sizeof(double) * std::max<int64_t>(1, sh.n()) * KP, gpu.pool, gpu.stream));
             {
                 const size_t n_tiles = static_cast<size_t>(std::max<int64_t>(1, sh.n_chunks())) * (data->lay.chunk / kSpTile);
-                MLB_CUDA(cudaMallocAsync(&eg.ll_tile, sizeof(double) * n_tiles, gpu.stream));
+                MLB_CUDA(cudaMallocFromPoolAsync(&eg.ll_tile, sizeof(double) * n_tiles, gpu.pool, gpu.stream));
                 MLB_CUDA(cudaMemsetAsync(eg.ll_tile, 0, sizeof(double) * n_tiles, gpu.stream));
             }
             MLB_CUDA(cudaMemsetAsync(eg.partials, 0, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.stream));
@@ -1021,6 +1025,7 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
 
 int mlb_em_destroy(mlb_em* em)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     if (!em) return MLB_OK;
     for (cudaGraphExec_t& ge : em->step_graph)
         if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
@@ -1036,12 +1041,14 @@ int mlb_em_destroy(mlb_em* em)
                           static_cast<void*>(eg.feat_e_off)})
             if (ptr) cudaFreeAsync(ptr, em->ctx->gpus[g].stream);
     }
+    em->reduce_scratch.release(em->ctx);
     delete em;
     return MLB_OK;
 }
 
 int mlb_em_set_params(mlb_em* em, const double* means, const double* covariances, const double* weights)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && means && covariances && weights, "mlb_em_set_params: null argument");
     const size_t dk = static_cast<size_t>(em->d) * em->k, kdd = static_cast<size_t>(em->k) * em->d * em->d;
     MLB_TRY(for_each_gpu(em->ctx, [&](int g, Gpu& gpu) -> int {
@@ -1059,6 +1066,7 @@ int mlb_em_set_params(mlb_em* em, const double* means, const double* covariances
 
 int mlb_em_run_steps(mlb_em* em, int steps, double* log_likelihoods)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && steps >= 0, "mlb_em_run_steps: bad argument");
     MLB_REQUIRE(steps <= kLlRing, "mlb_em_run_steps: at most %d steps per call", kLlRing);
     if (!em->have_params) { set_error("mlb_em_run_steps: parameters not set"); return MLB_ESTATE; }
@@ -1079,12 +1087,14 @@ int mlb_em_run_steps(mlb_em* em, int steps, double* log_likelihoods)
 
 int mlb_em_step(mlb_em* em, double* log_likelihood)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && log_likelihood, "mlb_em_step: null argument");
     return mlb_em_run_steps(em, 1, log_likelihood);
 }
 
 int mlb_em_get_params(mlb_em* em, double* means, double* covariances, double* weights)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em, "mlb_em_get_params: null argument");
     if (!em->have_params) { set_error("mlb_em_get_params: parameters not set"); return MLB_ESTATE; }
     Gpu& gpu = em->ctx->gpus[0];
@@ -1098,6 +1108,7 @@ int mlb_em_get_params(mlb_em* em, double* means, double* covariances, double* we
 
 int mlb_em_get_precisions(mlb_em* em, double* inverse_covariances, double* sqrt_determinants)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em, "mlb_em_get_precisions: null argument");
     if (!em->have_params) { set_error("mlb_em_get_precisions: parameters not set"); return MLB_ESTATE; }
     Gpu& gpu = em->ctx->gpus[0];
@@ -1111,22 +1122,44 @@ int mlb_em_get_precisions(mlb_em* em, double* inverse_covariances, double* sqrt_
 
 int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && cov_out, "mlb_em_sample_covariance: null argument");
     // A one-component M-step with unit responsibilities: theta = 0 for component 0, -inf constants elsewhere.
-    // Uses the spare theta slot and leaves the current parameters untouched.
-    const int d = em->d, DP = em->DP, KP = em->KP;
+    // Uses the spare theta slot and leaves the current parameters untouched.  On the fused path the pass runs the
+    // 8-component instantiation of the step kernel (a quarter of the tensor-pipe work of a K = 32 step); the chunk
+    // partials, the reduction and the exchange are the usual ones with the shorter statistics vector.
+    const int d = em->d, DP = em->DP;
+    const bool narrow = em->path == 1 && em->KP > 8;
+    const int KP = narrow ? 8 : em->KP, SV = narrow ? em_sv(DP, 8) : em->SV;
     std::vector<double> theta(em_theta_len(DP, KP), 0.0);
     for (int kk = 1; kk < KP; ++kk) theta[static_cast<size_t>(em->NE) * (KP / 8) * 32 + kk] = -std::numeric_limits<double>::infinity();
     MLB_TRY(for_each_gpu(em->ctx, [&](int g, Gpu& gpu) -> int {
         MLB_CUDA(cudaMemcpyAsync(em->gpus[g].theta[em->cur ^ 1], theta.data(), sizeof(double) * theta.size(), cudaMemcpyHostToDevice, gpu.stream));
-        return launch_pass(em, g, em->gpus[g].theta[em->cur ^ 1], false);
+        if (!narrow) return launch_pass(em, g, em->gpus[g].theta[em->cur ^ 1], false);
+        const EmKernelFn fn = em_kernel_for<0>(DP, 8);
+        const size_t smem = DP <= 8 ? em_small_smem_bytes(DP, 8) : em_smem_bytes(DP, 8);
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int per_sm = 0, sms = 0;
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), kEmThreads, smem));
+        MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
+        MLB_REQUIRE(per_sm >= 1, "mlb_em_sample_covariance: kernel does not fit on an SM");
+        EmArgs a = base_args(em, g);
+        a.theta = em->gpus[g].theta[em->cur ^ 1];
+        a.k = 1;
+        MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
+        if (a.n_chunks > 0) {
+            fn<<<std::min(per_sm * sms, a.n_chunks), kEmThreads, smem, gpu.stream>>>(a);
+            MLB_CUDA(cudaGetLastError());
+            ++em->launches;
+        }
+        return MLB_OK;
     }));
     if (em->path == 2) em->have_step = false;   // the pass overwrote the stored responsibilities
     std::vector<double*> partials, vsum;
     for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
-    MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV));
+    MLB_TRY(reduce_and_exchange(em->data, partials, vsum, SV, em->reduce_scratch));
     em->launches += static_cast<int64_t>(em->ctx->gpus.size());
-    std::vector<double> host(static_cast<size_t>(kVirtualShards) * em->SV);
+    std::vector<double> host(static_cast<size_t>(kVirtualShards) * SV);
     Gpu& gpu0 = em->ctx->gpus[0];
     MLB_CUDA(cudaSetDevice(gpu0.device));
     MLB_CUDA(cudaMemcpyAsync(host.data(), em->gpus[0].vsum, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, gpu0.stream));
@@ -1135,7 +1168,7 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
     std::vector<double> m1(d, 0.0), m2(static_cast<size_t>(d) * d, 0.0);
     for (size_t f = 0; f < em->feat_m.size(); ++f) {
         const int2 ab = em->feat_m[f];
-        const double val = tree8(host.data() + f * KP, em->SV);
+        const double val = tree8(host.data() + f * KP, SV);
         if (ab.x == DP && ab.y == DP) count = val;
         else if (ab.y == DP && ab.x < d) m1[ab.x] = val;
         else if (ab.x < d && ab.y < d) { m2[ab.x + static_cast<size_t>(ab.y) * d] = val; m2[ab.y + static_cast<size_t>(ab.x) * d] = val; }
@@ -1149,6 +1182,7 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
 
 int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t ld)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && resp, "mlb_em_mstep_from_responsibilities: null argument");
     mlb_ctx* ctx = em->ctx;
     const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
@@ -1156,7 +1190,7 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
     const int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         const DataShard& sh = em->data->shards[g];
         const int64_t n = std::max<int64_t>(1, sh.n());
-        MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dev[g], sizeof(double) * n * em->k, gpu.pool, gpu.stream));
         if (sh.n() > 0)
             MLB_TRY(staged_h2d(gpu, dev[g], resp + (sh.begin - host_begin), static_cast<size_t>(em->k), sizeof(double) * sh.n(), sizeof(double) * ld));
         return MLB_OK;
@@ -1166,6 +1200,7 @@ int mlb_em_mstep_from_responsibilities(mlb_em* em, const double* resp, int64_t l
 
 int mlb_em_mstep_from_labels(mlb_em* em, const unsigned int* labels)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && labels, "mlb_em_mstep_from_labels: null argument");
     mlb_ctx* ctx = em->ctx;
     const int64_t host_begin = ctx->rank_mode ? em->data->shards[0].begin : 0;
@@ -1181,8 +1216,8 @@ int mlb_em_mstep_from_labels(mlb_em* em, const unsigned int* labels)
     const int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         const DataShard& sh = em->data->shards[g];
         const int64_t n = std::max<int64_t>(1, sh.n());
-        MLB_CUDA(cudaMallocAsync(&dev[g], sizeof(double) * n * em->k, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&dev_labels[g], sizeof(unsigned) * n, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dev[g], sizeof(double) * n * em->k, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dev_labels[g], sizeof(unsigned) * n, gpu.pool, gpu.stream));
         if (sh.n() > 0) {
             MLB_TRY(staged_h2d(gpu, dev_labels[g], labels + (sh.begin - host_begin), 1, sizeof(unsigned) * sh.n(), sizeof(unsigned) * sh.n()));
             em_onehot_kernel<<<static_cast<unsigned>((sh.n() + 255) / 256), 256, 0, gpu.stream>>>(dev_labels[g], sh.n(), em->k, dev[g]);
@@ -1198,6 +1233,7 @@ int mlb_em_mstep_from_labels(mlb_em* em, const unsigned int* labels)
 
 int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out, int64_t ld, unsigned int* labels_out)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em, "mlb_em_emit_range: null argument");
     MLB_REQUIRE(begin >= 0 && count >= 0 && begin + count <= em->data->lay.n_total, "mlb_em_emit_range: range out of bounds");
     if (!em->have_step) { set_error("mlb_em_emit: no step has been run"); return MLB_ESTATE; }
@@ -1210,8 +1246,8 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
     // Stage by stage: kStagePoints points per GPU at a time through a device buffer.
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         EmGpu& eg = em->gpus[g];
-        if (resp_out && !eg.stage) MLB_CUDA(cudaMallocAsync(&eg.stage, sizeof(double) * kStagePoints * em->k, gpu.stream));
-        if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMallocAsync(&eg.stage_labels, sizeof(unsigned) * kStagePoints, gpu.stream));
+        if (resp_out && !eg.stage) MLB_CUDA(cudaMallocFromPoolAsync(&eg.stage, sizeof(double) * kStagePoints * em->k, gpu.pool, gpu.stream));
+        if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMallocFromPoolAsync(&eg.stage_labels, sizeof(unsigned) * kStagePoints, gpu.pool, gpu.stream));
         return MLB_OK;
     }));
     for (int64_t off = 0;; off += kStagePoints) {
@@ -1261,6 +1297,7 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
 
 int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_out)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em, "mlb_em_emit: null argument");
     const std::vector<DataShard>& shards = em->data->shards;
     return mlb_em_emit_range(em, shards.front().begin, shards.back().end - shards.front().begin, resp_out, ld, labels_out);
@@ -1268,6 +1305,7 @@ int mlb_em_emit(mlb_em* em, double* resp_out, int64_t ld, unsigned int* labels_o
 
 int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double* resp_out, int64_t ld_out, unsigned int* labels_out)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && x, "mlb_em_predict: null argument");
     MLB_REQUIRE(m >= 0 && ld_x >= em->d, "mlb_em_predict: bad shape (m=%lld, ld_x=%lld, D=%d)", static_cast<long long>(m), static_cast<long long>(ld_x), em->d);
     MLB_REQUIRE(!resp_out || ld_out >= m, "mlb_em_predict: leading dimension smaller than the row count");
@@ -1278,16 +1316,16 @@ int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double*
     EmGpu& eg = em->gpus[0];
     const int d = em->d;
     MLB_CUDA(cudaSetDevice(gpu.device));
-    if (resp_out && !eg.stage) MLB_CUDA(cudaMallocAsync(&eg.stage, sizeof(double) * kStagePoints * em->k, gpu.stream));
-    if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMallocAsync(&eg.stage_labels, sizeof(unsigned) * kStagePoints, gpu.stream));
+    if (resp_out && !eg.stage) MLB_CUDA(cudaMallocFromPoolAsync(&eg.stage, sizeof(double) * kStagePoints * em->k, gpu.pool, gpu.stream));
+    if (labels_out && !eg.stage_labels) MLB_CUDA(cudaMallocFromPoolAsync(&eg.stage_labels, sizeof(unsigned) * kStagePoints, gpu.pool, gpu.stream));
     const int64_t cap = std::min<int64_t>(m, kStagePoints);
     double *xd = nullptr, *r_tmp = nullptr, *ll_tmp = nullptr;
-    MLB_CUDA(cudaMallocAsync(&xd, sizeof(double) * cap * d, gpu.stream));
+    MLB_CUDA(cudaMallocFromPoolAsync(&xd, sizeof(double) * cap * d, gpu.pool, gpu.stream));
     int rc = MLB_OK;
     auto body = [&]() -> int {
         if (em->path == 2) {
-            MLB_CUDA(cudaMallocAsync(&r_tmp, sizeof(double) * cap * em->KP, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&ll_tmp, sizeof(double) * ((cap + 127) / 128) * 2, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&r_tmp, sizeof(double) * cap * em->KP, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&ll_tmp, sizeof(double) * ((cap + 127) / 128) * 2, gpu.pool, gpu.stream));
         }
         for (int64_t off = 0; off < m; off += kStagePoints) {
             const int64_t n = std::min<int64_t>(kStagePoints, m - off);
@@ -1354,6 +1392,7 @@ int mlb_em_set_kernel_timing(mlb_em* em, int enabled)
 
 int mlb_em_kernel_time_ms(mlb_em* em, double* total_ms, int64_t* launches)
 {
+    MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em, "mlb_em_kernel_time_ms: null argument");
     MLB_CUDA(cudaSetDevice(em->ctx->gpus[0].device));
     return em->gpus[0].timer.total(total_ms, launches);

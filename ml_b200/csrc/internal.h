@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -70,7 +71,7 @@ const NcclApi* nccl();
     } while (0)
 
 constexpr int kVirtualShards = MLB_VIRTUAL_SHARDS;
-constexpr int kCopyThreadsMax = 4;   // host threads that pack / unpack the pinned bounce buffers of one large copy
+constexpr int kCopyThreadsMax = 8;   // host threads that pack / unpack the pinned bounce buffers of one large copy
 constexpr int kSmCount = 148;  // B200
 
 // e / d for 0 <= e < 65536 and 1 <= d <= 128 without the ~30-instruction integer division the compiler emits for a
@@ -99,6 +100,7 @@ struct Gpu {
     int device = 0;
     int rank = 0;  // global rank of this GPU in [0, world)
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;  // the context's own stream-ordered allocation pool on this device
     ncclComm_t comm = nullptr;  // null when world == 1
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // pinned bounce buffers for copies from / to pageable host memory (staged_h2d, staged_d2h): two per copy thread
@@ -112,8 +114,20 @@ struct mlb_ctx {
     int world = 1;          // total GPUs in the job
     bool rank_mode = false; // one process per GPU
     std::vector<mlb::Gpu> gpus;  // the local ones, consecutive ranks
+    // Every C-ABI entry point that enqueues work holds this for its whole duration: the context owns ONE stream and
+    // ONE set of pinned bounce buffers per GPU, and EM captures its step into a CUDA graph on that stream, so two
+    // host threads driving two models (cppyml releases the GIL inside fit) must not interleave inside a call.
+    // Recursive: entry points call each other (mlb_em_step -> mlb_em_run_steps -> mlb_ctx_synchronize).
+    std::recursive_mutex mu;
     int vshards_per_gpu() const { return mlb::kVirtualShards / world; }
 };
+
+// First statement of every C-ABI entry point that touches a context (ctx_ may be null: the argument checks that follow
+// report it): serialises on the context and restores the caller's current CUDA device on return.
+#define MLB_ENTER(ctx_)                                        \
+    ::mlb::DeviceRestore mlb_dev_;                             \
+    std::unique_lock<std::recursive_mutex> mlb_lock_;          \
+    if (mlb_ctx* mlb_c_ = (ctx_)) mlb_lock_ = std::unique_lock<std::recursive_mutex>(mlb_c_->mu)
 
 namespace mlb {
 
@@ -124,8 +138,6 @@ struct DataShard {
     int64_t begin = 0, end = 0;           // global point range
     int64_t chunk_begin = 0, chunk_end = 0;  // global chunk range
     double* shift = nullptr;   // d doubles: the global data mean (device copy)
-    double* reduce_scratch = nullptr;  // level-1 group sums of reduce_and_exchange (grown on demand)
-    size_t reduce_scratch_len = 0;
     double* nearest = nullptr;        // K-means++ seeding: squared distance to the nearest chosen centroid, per local point (seeding.cu)
     double* seed_centroid = nullptr;  // d doubles: the newest centroid of the seeding pass
     int64_t n() const { return end - begin; }
@@ -145,6 +157,13 @@ struct mlb_data {
 
 namespace mlb {
 
+// Restores the caller's current CUDA device when a C-ABI call returns (the library switches devices internally).
+struct DeviceRestore {
+    int saved = -1;
+    DeviceRestore() { if (cudaGetDevice(&saved) != cudaSuccess) { saved = -1; cudaGetLastError(); } }
+    ~DeviceRestore() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
 // Runs body(g, gpu) for every local GPU with that GPU's device made current.
 template <class F>
 int for_each_gpu(mlb_ctx* ctx, F&& body)
@@ -156,11 +175,20 @@ int for_each_gpu(mlb_ctx* ctx, F&& body)
     return MLB_OK;
 }
 
+// Level-1 group sums of reduce_and_exchange, one buffer per local GPU, grown on demand.  Owned by the object whose
+// statistics are reduced (mlb_em, mlb_km), never shared: EM replays its step from a CUDA graph that has the buffer's
+// address baked in, so nobody else may reallocate it.
+struct ReduceScratch {
+    std::vector<double*> ptr;
+    std::vector<size_t> len;
+    void release(mlb_ctx* ctx);
+};
+
 // Reduces per-chunk partial vectors to the 8 virtual-shard vectors and exchanges them.
 //   partials[g]: device, [local chunks of GPU g][s]
 //   vsum[g]:     device, [8][s]; on return every GPU holds all 8 shard vectors.
 // Fixed summation order => deterministic and independent of the GPU count.
-int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s);
+int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s, ReduceScratch& scratch);
 
 // Copies between host memory that is probably pageable (a numpy array, a std::vector, an Eigen matrix) and the device.
 // A direct cudaMemcpy of pageable memory runs at ~10 GB/s host -> device and ~4 GB/s device -> host on these boxes (one
@@ -170,8 +198,9 @@ int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, co
 // the bound.  Pinned host memory (cudaMallocHost / cudaHostRegister) and small copies go straight to cudaMemcpyAsync.
 //
 // staged_h2d: the source is `rows` rows of `row_bytes` bytes, `src_stride` bytes apart (src_stride == row_bytes: one
-// contiguous block); the destination is dense.  On return the source has been read completely (the caller may free
-// it); the DMAs are ordered on gpu.stream like any other work.
+// contiguous block); the destination is dense.  The DMAs are ordered on gpu.stream like any other work.  A pageable
+// source has been read completely on return; a PINNED source is read by the DMA engine asynchronously, so the caller
+// must synchronise the stream (every C-ABI entry point does, on all of its exit paths) before the buffer may go away.
 int staged_h2d(Gpu& gpu, void* dst_device, const void* src, size_t rows, size_t row_bytes, size_t src_stride);
 // staged_d2h: synchronous; on return dst holds the data.
 int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes);

@@ -744,6 +744,7 @@ struct mlb_km {
     size_t smem = 0, smem_stats = 0;
     bool have_centroids = false, have_stats = false;
     int64_t launches = 0;
+    ReduceScratch reduce_scratch;
 };
 
 namespace mlb {
@@ -819,6 +820,7 @@ extern "C" {
 
 int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
 {
+    MLB_ENTER(ctx);
     MLB_REQUIRE(ctx && data && out, "mlb_km_create: null argument");
     MLB_REQUIRE(data->ctx == ctx, "mlb_km_create: data belongs to another context");
     MLB_REQUIRE(k >= 1, "mlb_km_create: number of clusters must be positive");
@@ -862,25 +864,25 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         KmGpu& kg = km->gpus[g];
         const DataShard& sh = data->shards[g];
-        MLB_CUDA(cudaMallocAsync(&kg.craw, sizeof(double) * d * k, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.cold, sizeof(double) * d * k, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.cfrag, sizeof(double) * DP * KP, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.cnorm, sizeof(double) * KP, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.cmax, sizeof(double) * km->nblocks, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.craw, sizeof(double) * d * k, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cold, sizeof(double) * d * k, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cfrag, sizeof(double) * DP * KP, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cnorm, sizeof(double) * KP, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cmax, sizeof(double) * km->nblocks, gpu.pool, gpu.stream));
         if (km->nblocks > 1) {
             const int64_t n = std::max<int64_t>(1, sh.n());
-            MLB_CUDA(cudaMallocAsync(&kg.best_lab, sizeof(unsigned) * n, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&kg.best_dist, sizeof(double) * n, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&kg.lab_tmp, sizeof(unsigned) * n, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&kg.dist_tmp, sizeof(double) * n, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&kg.scratch, sizeof(double) * 8 * std::max<int64_t>(1, sh.n_chunks()), gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&kg.best_lab, sizeof(unsigned) * n, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&kg.best_dist, sizeof(double) * n, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&kg.lab_tmp, sizeof(unsigned) * n, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&kg.dist_tmp, sizeof(double) * n, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&kg.scratch, sizeof(double) * 8 * std::max<int64_t>(1, sh.n_chunks()), gpu.pool, gpu.stream));
             MLB_CUDA(cudaMemsetAsync(kg.lab_tmp, 0, sizeof(unsigned) * n, gpu.stream));
         }
-        MLB_CUDA(cudaMallocAsync(&kg.labels, sizeof(unsigned) * std::max<int64_t>(1, sh.n()), gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.vsum, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.out, sizeof(double) * 4, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&kg.counter, sizeof(unsigned), gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.labels, sizeof(unsigned) * std::max<int64_t>(1, sh.n()), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.vsum, sizeof(double) * kVirtualShards * km->SV, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.out, sizeof(double) * 4, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.counter, sizeof(unsigned), gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(kg.labels, 0, sizeof(unsigned) * std::max<int64_t>(1, sh.n()), gpu.stream));   // labels_.resize(): zeros
         MLB_CUDA(cudaMemsetAsync(kg.vsum, 0, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(kg.cold, 0, sizeof(double) * d * k, gpu.stream));
@@ -905,6 +907,7 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
 
 int mlb_km_destroy(mlb_km* km)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     if (!km) return MLB_OK;
     for (size_t g = 0; g < km->gpus.size(); ++g) {
         cudaSetDevice(km->ctx->gpus[g].device);
@@ -917,12 +920,14 @@ int mlb_km_destroy(mlb_km* km)
                           static_cast<void*>(kg.lab_tmp), static_cast<void*>(kg.dist_tmp), static_cast<void*>(kg.scratch)})
             if (ptr) cudaFreeAsync(ptr, km->ctx->gpus[g].stream);
     }
+    km->reduce_scratch.release(km->ctx);
     delete km;
     return MLB_OK;
 }
 
 int mlb_km_set_centroids(mlb_km* km, const double* centroids)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     MLB_REQUIRE(km && centroids, "mlb_km_set_centroids: null argument");
     MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
         MLB_CUDA(cudaMemcpyAsync(km->gpus[g].craw, centroids, sizeof(double) * km->d * km->k, cudaMemcpyHostToDevice, gpu.stream));
@@ -937,6 +942,7 @@ int mlb_km_set_centroids(mlb_km* km, const double* centroids)
 
 int mlb_km_get_centroids(mlb_km* km, double* centroids)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     MLB_REQUIRE(km && centroids, "mlb_km_get_centroids: null argument");
     if (!km->have_centroids) { set_error("mlb_km_get_centroids: centroids not set"); return MLB_ESTATE; }
     Gpu& gpu = km->ctx->gpus[0];
@@ -948,6 +954,7 @@ int mlb_km_get_centroids(mlb_km* km, double* centroids)
 
 int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     MLB_REQUIRE(km, "mlb_km_assign: null argument");
     if (!km->have_centroids) { set_error("mlb_km_assign: centroids not set"); return MLB_ESTATE; }
     mlb_ctx* ctx = km->ctx;
@@ -977,7 +984,7 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
     }));
     std::vector<double*> partials, vsum;
     for (KmGpu& kg : km->gpus) { partials.push_back(kg.partials); vsum.push_back(kg.vsum); }
-    MLB_TRY(reduce_and_exchange(km->data, partials, vsum, km->SV));
+    MLB_TRY(reduce_and_exchange(km->data, partials, vsum, km->SV, km->reduce_scratch));
     km->launches += static_cast<int64_t>(ctx->gpus.size());
     double host[4] = {0, 0, 0, 0};
     {
@@ -997,6 +1004,7 @@ int mlb_km_assign(mlb_km* km, double* inertia, int64_t* n_changed)
 
 int mlb_km_update(mlb_km* km, double* centroid_shift_sq)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     MLB_REQUIRE(km, "mlb_km_update: null argument");
     if (!km->have_stats) { set_error("mlb_km_update: no assignment to update from"); return MLB_ESTATE; }
     MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
@@ -1020,6 +1028,7 @@ int mlb_km_update(mlb_km* km, double* centroid_shift_sq)
 
 int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigned int* labels_out, double* sqdist_out)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     MLB_REQUIRE(km && x && labels_out, "mlb_km_predict: null argument");
     MLB_REQUIRE(m >= 0 && ld_x >= km->d, "mlb_km_predict: bad shape (m=%lld, ld_x=%lld, D=%d)", static_cast<long long>(m), static_cast<long long>(ld_x), km->d);
     if (!km->have_centroids) { set_error("mlb_km_predict: centroids not set"); return MLB_ESTATE; }
@@ -1034,16 +1043,16 @@ int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigne
     double *xd = nullptr, *dist = nullptr, *partials = nullptr, *tmp_dist = nullptr, *tmp_scratch = nullptr;
     unsigned *labels = nullptr, *tmp_best_lab = nullptr, *tmp_lab = nullptr;
     auto body = [&]() -> int {
-        MLB_CUDA(cudaMallocAsync(&xd, sizeof(double) * cap * d, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&dist, sizeof(double) * cap, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&labels, sizeof(unsigned) * cap, gpu.stream));
-        MLB_CUDA(cudaMallocAsync(&partials, sizeof(double) * 8 * cap_chunks, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&xd, sizeof(double) * cap * d, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dist, sizeof(double) * cap, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&labels, sizeof(unsigned) * cap, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&partials, sizeof(double) * 8 * cap_chunks, gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(labels, 0, sizeof(unsigned) * cap, gpu.stream));   // the kernel reads the "previous" labels
         if (km->nblocks > 1) {
-            MLB_CUDA(cudaMallocAsync(&tmp_best_lab, sizeof(unsigned) * cap, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&tmp_lab, sizeof(unsigned) * cap, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&tmp_dist, sizeof(double) * cap, gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&tmp_scratch, sizeof(double) * 8 * cap_chunks, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&tmp_best_lab, sizeof(unsigned) * cap, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&tmp_lab, sizeof(unsigned) * cap, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&tmp_dist, sizeof(double) * cap, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&tmp_scratch, sizeof(double) * 8 * cap_chunks, gpu.pool, gpu.stream));
             MLB_CUDA(cudaMemsetAsync(tmp_lab, 0, sizeof(unsigned) * cap, gpu.stream));
         }
         for (int64_t off = 0; off < m; off += kStage) {
@@ -1066,6 +1075,7 @@ int mlb_km_predict(mlb_km* km, const double* x, int64_t m, int64_t ld_x, unsigne
 
 int mlb_km_get_labels(mlb_km* km, unsigned int* labels)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     MLB_REQUIRE(km && labels, "mlb_km_get_labels: null argument");
     const int64_t host_begin = km->ctx->rank_mode ? km->data->shards[0].begin : 0;
     MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
@@ -1088,6 +1098,7 @@ int mlb_km_set_kernel_timing(mlb_km* km, int enabled)
 
 int mlb_km_kernel_time_ms(mlb_km* km, double* total_ms, int64_t* launches)
 {
+    MLB_ENTER(km ? km->ctx : nullptr);
     MLB_REQUIRE(km, "mlb_km_kernel_time_ms: null argument");
     MLB_CUDA(cudaSetDevice(km->ctx->gpus[0].device));
     return km->gpus[0].timer.total(total_ms, launches);

@@ -74,6 +74,7 @@ extern "C" {
 
 int mlb_data_kpp_update(mlb_data* data, const double* centroid, int first, double* nearest_out)
 {
+    MLB_ENTER(data ? data->ctx : nullptr);
     MLB_REQUIRE(data && centroid, "mlb_data_kpp_update: null argument");
     const int d = data->d;
     MLB_REQUIRE(d <= 128, "mlb_data_kpp_update: D=%d not supported by this build (D <= 128)", d);
@@ -83,8 +84,8 @@ int mlb_data_kpp_update(mlb_data* data, const double* centroid, int first, doubl
         DataShard& sh = data->shards[g];
         if (!sh.nearest) {
             MLB_REQUIRE(first, "mlb_data_kpp_update: the first call on a data set must pass first != 0");
-            MLB_CUDA(cudaMallocAsync(&sh.nearest, sizeof(double) * std::max<int64_t>(1, sh.n()), gpu.stream));
-            MLB_CUDA(cudaMallocAsync(&sh.seed_centroid, sizeof(double) * d, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&sh.nearest, sizeof(double) * std::max<int64_t>(1, sh.n()), gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&sh.seed_centroid, sizeof(double) * d, gpu.pool, gpu.stream));
             MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kpp_nearest_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         }
         MLB_CUDA(cudaMemcpyAsync(sh.seed_centroid, centroid, sizeof(double) * d, cudaMemcpyHostToDevice, gpu.stream));

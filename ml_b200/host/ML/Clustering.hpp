@@ -90,6 +90,19 @@ namespace ml
 			DLL_DECLSPEC void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut centroids) const override;
 		};
 
+		/** The given D x K matrix, verbatim (an addition to the reference's set): lets a caller start every rank of a
+		multi-GPU job, or a benchmark, from exactly the same centroids without touching the pseudo-random stream. */
+		class ExplicitCentroids : public CentroidsInitialiser
+		{
+		public:
+			DLL_DECLSPEC explicit ExplicitCentroids(Eigen::MatrixXd centroids);
+
+			/** @throw std::invalid_argument If the stored matrix is not D x number_components. */
+			DLL_DECLSPEC void init(DataView data, Prng& prng, unsigned int number_components, MatrixOut centroids) const override;
+		private:
+			Eigen::MatrixXd centroids_;
+		};
+
 		/** One-hot responsibilities: every point belongs to its nearest initial centroid. */
 		class ClosestCentroid : public ResponsibilitiesInitialiser
 		{

@@ -11,8 +11,10 @@
 //   - assign_responsibilities(points): the batched form of assign_responsibilities(x, u), on the device;
 //   - the built-in KPP and ClosestCentroid initialisers run their O(N K D) distance passes on the device (the draws
 //     stay on the host with the model's PRNG, so the initial state is the reference's);
-//   - responsibilities() is out of line: the N x K matrix stays on the device until first asked for
-//     (25.6 GB at N=1e8, K=32), then is materialised once; the values are the reference's.
+//   - responsibilities() and labels() are out of line: the N x K matrix (25.6 GB at N=1e8, K=32) and the N labels
+//     (400 MB) stay on the device until first asked for, then are materialised once; the values are the reference's;
+//   - shapes: any K; D <= 128 (the device refresh of a component factorises its D x D covariance inside one SM);
+//     larger D makes fit() throw std::invalid_argument.
 #include <memory>
 #include <random>
 #include <vector>
@@ -96,7 +98,9 @@ namespace ml
 		@throw std::logic_error If there is no fitted device state (no fit yet, or the N == K exact fit). */
 		DLL_DECLSPEC Eigen::MatrixXd assign_responsibilities(DataView points) const;
 
-		const std::vector<unsigned int>& labels() const override { return labels_; }
+		/** Brought from the device on first access after a converged fit; like the reference, a fit that did not
+		converge leaves no meaningful labels (N zeros). */
+		DLL_DECLSPEC const std::vector<unsigned int>& labels() const override;
 
 		bool converged() const override { return converged_; }
 
@@ -113,7 +117,9 @@ namespace ml
 		std::vector<Eigen::MatrixXd> covariances_; /**< K matrices D x D */
 		std::vector<Eigen::MatrixXd> inverse_covariances_;
 		Eigen::VectorXd sqrt_covariance_determinants_;
-		std::vector<unsigned int> labels_;
+		mutable std::vector<unsigned int> labels_;
+		mutable bool labels_on_host_;
+		Eigen::Index sample_size_;
 		double absolute_tolerance_;
 		double relative_tolerance_;
 		double log_likelihood_;

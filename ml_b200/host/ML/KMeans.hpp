@@ -28,7 +28,8 @@ namespace ml
 
             unsigned int number_clusters() const override { return number_clusters_; }
 
-            const std::vector<unsigned int>& labels() const override { return labels_; }
+            /** Brought from the device on first access after a fit (400 MB at N = 1e8). */
+            DLL_DECLSPEC const std::vector<unsigned int>& labels() const override;
 
             const Eigen::MatrixXd& centroids() const override { return centroids_; }
 
@@ -66,7 +67,8 @@ namespace ml
             /** Assignment steps executed by the last (single-initialisation) fit. */
             unsigned int number_iterations() const { return number_iterations_; }
         private:
-            std::vector<unsigned int> labels_;
+            mutable std::vector<unsigned int> labels_;
+            mutable bool labels_on_host_;
             Eigen::MatrixXd centroids_;
             Prng prng_;
             std::shared_ptr<const CentroidsInitialiser> centroids_initialiser_;

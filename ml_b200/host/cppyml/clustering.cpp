@@ -14,6 +14,7 @@
 #include <stdexcept>
 
 #include "ML/Clustering.hpp"
+#include "ML/Distributed.hpp"
 #include "ML/EM.hpp"
 #include "ML/KMeans.hpp"
 
@@ -48,6 +49,24 @@ namespace
 		py::array_t<double, py::array::f_style> out({m.rows(), m.cols()});
 		std::memcpy(out.mutable_data(), m.data(), sizeof(double) * static_cast<size_t>(m.size()));
 		return out;
+	}
+
+	py::array_t<unsigned int> to_numpy(const std::vector<unsigned int>& v)
+	{
+		py::array_t<unsigned int> out(static_cast<py::ssize_t>(v.size()));
+		std::memcpy(out.mutable_data(), v.data(), sizeof(unsigned int) * v.size());
+		return out;
+	}
+
+	/** (K, D) C-contiguous array -> D x K column-major matrix (the same memory). */
+	Eigen::MatrixXd centroids_from_rows(const py::array_t<double, py::array::c_style | py::array::forcecast>& rows)
+	{
+		if (rows.ndim() != 2) {
+			throw py::type_error("centroids must be a 2-D array of shape (K, D)");
+		}
+		Eigen::MatrixXd m(rows.shape(1), rows.shape(0));
+		std::memcpy(m.data(), rows.data(), sizeof(double) * static_cast<size_t>(m.size()));
+		return m;
 	}
 
 	py::array_t<double> to_numpy(const Eigen::VectorXd& v)
@@ -168,6 +187,12 @@ void init_clustering(py::module_& m)
 		.def(py::init<>())
 		.doc() = "k-means++ seeding: each new centroid is a data point drawn with probability proportional to its squared distance from the centroids chosen so far (distance passes on the GPU).";
 
+	py::class_<ml::Clustering::ExplicitCentroids, std::shared_ptr<ml::Clustering::ExplicitCentroids>, ml::Clustering::CentroidsInitialiser>(m_clustering, "ExplicitCentroids")
+		.def(py::init([](const py::array_t<double, py::array::c_style | py::array::forcecast>& centroids) {
+			return std::make_shared<ml::Clustering::ExplicitCentroids>(centroids_from_rows(centroids));
+		}), py::arg("centroids"))
+		.doc() = "The given (K, D) array, verbatim, as the starting centroids (an addition to the reference's initialisers).";
+
 	py::class_<ml::Clustering::ClosestCentroid, std::shared_ptr<ml::Clustering::ClosestCentroid>, ml::Clustering::ResponsibilitiesInitialiser>(m_clustering, "ClosestCentroid")
 		.def(py::init<std::shared_ptr<ml::Clustering::CentroidsInitialiser>>(), py::arg("centroids_initialiser"))
 		.doc() = "One-hot responsibilities: each point belongs to the nearest of the centroids its centroids_initialiser picks.";
@@ -186,10 +211,24 @@ void init_clustering(py::module_& m)
 			"Runs EM on the GPU.\n\nArgs:\n    data: float64 C-contiguous array of shape (N, D), one point per row; used as is, never converted.\n\nReturns:\n    Whether the log-likelihood change fell below the tolerance before maximum_steps.")
 		.def_property_readonly("number_components", &ml::EMPy::number_components, "K, as given to the constructor.")
 		.def_property_readonly("means", [](const ml::EMPy& em) { return to_numpy(em.means()); }, "Means after the fit, shape (D, K).")
-		.def_property_readonly("responsibilities", [](const ml::EMPy& em) { return to_numpy(em.responsibilities()); }, "Responsibilities of the last E-step, shape (N, K); brought to the host on first access.")
+		.def_property_readonly("responsibilities", [](py::object self) {
+			// A read-only view of the model's own N x K matrix (what pybind11/eigen.h returns for a `const MatrixXd&`
+			// property in the reference): no second copy of a matrix that is 25.6 GB at N = 1e8, K = 32.
+			const ml::EMPy& em = self.cast<const ml::EMPy&>();
+			const Eigen::MatrixXd* r = nullptr;
+			{
+				py::gil_scoped_release release;
+				r = &em.responsibilities();
+			}
+			py::array_t<double> view({r->rows(), r->cols()}, {static_cast<py::ssize_t>(sizeof(double)), static_cast<py::ssize_t>(sizeof(double) * r->rows())}, r->data(), self);
+			py::detail::array_proxy(view.ptr())->flags &= ~py::detail::npy_api::NPY_ARRAY_WRITEABLE_;
+			return view;
+		}, "Responsibilities of the last E-step, shape (N, K): a read-only view of the model's matrix, brought to the host on first access.")
 		.def_property_readonly("log_likelihood", &ml::EMPy::log_likelihood, "Mean log-likelihood per point at the last E-step.")
 		.def_property_readonly("mixing_probabilities", [](const ml::EMPy& em) { return to_numpy(em.mixing_probabilities()); }, "Mixture weights, shape (K,).")
 		.def_property_readonly("number_iterations", &ml::EMPy::number_iterations, "Iterations run by the last fit.")
+		.def_property_readonly("converged", &ml::EMPy::converged, "Whether the last fit converged.")
+		.def_property_readonly("labels_array", [](const ml::EMPy& em) { return to_numpy(em.labels()); }, "Most responsible component of every fitted point as a uint32 array (meaningful after a converged fit); brought to the host on first access.")
 		.def("covariance", [](const ml::EMPy& em, unsigned int k) { return to_numpy(em.covariance(k)); }, py::arg("k"),
 			"Args:\n    k: component index in [0, K).\n\nReturns:\n    The (D, D) covariance of that component.")
 		.def("assign_responsibilities", &ml::EMPy::calculate_responsibilities, py::arg("x"),
@@ -210,7 +249,8 @@ void init_clustering(py::module_& m)
 			"Runs Lloyd iterations on the GPU.\n\nArgs:\n    data: float64 C-contiguous array of shape (N, D), one point per row; used as is, never converted.\n\nReturns:\n    Whether the labels or the centroids stopped moving before maximum_steps.")
 		.def_property_readonly("number_clusters", &ml::Clustering::KMeansPy::number_clusters, "K, as given to the constructor.")
 		.def_property_readonly("centroids", &ml::Clustering::KMeansPy::centroids_row_major, "Centroids after the fit, shape (K, D).")
-		.def_property_readonly("labels", &ml::Clustering::KMeansPy::labels, "Cluster index of every fitted point.")
+		.def_property_readonly("labels", &ml::Clustering::KMeansPy::labels, "Cluster index of every fitted point (a list, as in the reference; brought to the host on first access).")
+		.def_property_readonly("labels_array", [](const ml::Clustering::KMeansPy& km) { return to_numpy(km.labels()); }, "The same as a uint32 numpy array (an addition: a Python list of 1e8 integers takes gigabytes).")
 		.def_property_readonly("inertia", &ml::Clustering::KMeansPy::inertia, "Sum of the squared distances of the points to their centroids.")
 		.def_property_readonly("converged", &ml::Clustering::KMeansPy::converged, "Whether the last fit converged.")
 		.def_property_readonly("number_iterations", &ml::Clustering::KMeansPy::number_iterations, "Assignment steps run by the last fit.")
@@ -219,4 +259,23 @@ void init_clustering(py::module_& m)
 		.def("assign_labels", &ml::Clustering::KMeansPy::assign_labels_py, py::arg("data").noconvert(),
 			"Assigns every row of data to its closest cluster (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    Tuple of the array of cluster labels and the array of squared Euclidean distances to the cluster centroids.")
 		.doc() = "Lloyd's K-means on B200 GPUs.";
+
+	auto m_distributed = m.def_submodule("distributed", "One process per GPU: every rank fits its own rows, parameters are exchanged over NCCL (an addition to the reference).");
+	m_distributed.def("unique_id", []() {
+		const auto id = ml::Distributed::unique_id();
+		return py::bytes(reinterpret_cast<const char*>(id.data()), id.size());
+	}, "The 128-byte NCCL id rank 0 creates and ships to the other ranks.");
+	m_distributed.def("init", [](int device, int rank, int world, const py::bytes& id) {
+		const std::string raw = id;
+		if (raw.size() != 128) {
+			throw py::value_error("the NCCL id must have 128 bytes");
+		}
+		std::array<unsigned char, 128> buffer{};
+		std::memcpy(buffer.data(), raw.data(), 128);
+		ml::Distributed::init(device, rank, world, buffer);
+	}, py::arg("device"), py::arg("rank"), py::arg("world"), py::arg("unique_id"), "Makes this process rank `rank` of `world` on CUDA device `device`; call before the first fit.");
+	m_distributed.def("shard_range", [](std::int64_t n_total, int world, int rank) {
+		const auto range = ml::Distributed::shard_range(n_total, world, rank);
+		return py::make_tuple(range.first, range.second);
+	}, py::arg("n_total"), py::arg("world"), py::arg("rank"), "Half-open range [begin, end) of the rows rank `rank` passes to fit().");
 }

@@ -4,4 +4,5 @@ Mirrors the package layout of the reference (cppyml/cppyml/__init__.py:18-21): t
 `cppyml.cppyml` holds the submodules.  Only `clustering` is provided here.
 """
 from .cppyml import clustering  # noqa: F401
+from .cppyml import distributed  # noqa: F401
 from .cppyml import __version__, backend  # noqa: F401

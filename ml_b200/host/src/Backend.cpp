@@ -1,4 +1,5 @@
 #include "Backend.hpp"
+#include "ML/Distributed.hpp"
 
 #include <algorithm>
 #include <cstdlib>
@@ -38,11 +39,27 @@ namespace ml
 			};
 		}
 
+		namespace
+		{
+			ContextHolder& context_holder()
+			{
+				static ContextHolder holder;
+				return holder;
+			}
+
+			std::mutex& context_mutex()
+			{
+				static std::mutex mutex;
+				return mutex;
+			}
+
+			bool distributed_active = false;
+		}
+
 		mlb_ctx* shared_context()
 		{
-			static ContextHolder holder;
-			static std::mutex mutex;
-			std::lock_guard<std::mutex> lock(mutex);
+			ContextHolder& holder = context_holder();
+			std::lock_guard<std::mutex> lock(context_mutex());
 			if (!holder.ctx) {
 				int number_devices = 1;
 				if (const char* env = std::getenv("MLPP_CUDA_DEVICES")) {
@@ -56,7 +73,13 @@ namespace ml
 		DeviceData::DeviceData(Eigen::Ref<const Eigen::MatrixXd> data)
 			: rows_(data.rows()), cols_(data.cols())
 		{
-			check(mlb_data_upload(shared_context(), data.data(), data.cols(), data.cols(), static_cast<int>(data.rows()), data.outerStride(), &handle_), "upload");
+			mlb_ctx* ctx = shared_context();
+			int64_t total = data.cols();
+			if (distributed_active) {
+				// one process per GPU: `data` holds this rank's columns, the problem is the concatenation over the ranks
+				check(mlb_ctx_sum_int64(ctx, data.cols(), &total), "point count over the ranks");
+			}
+			check(mlb_data_upload(ctx, data.data(), data.cols(), total, static_cast<int>(data.rows()), data.outerStride(), &handle_), "upload");
 		}
 
 		DeviceData::~DeviceData()
@@ -242,6 +265,41 @@ namespace ml
 		{
 			labels.resize(static_cast<size_t>(data_->cols()));
 			check(mlb_km_get_labels(km_, labels.data()), "KMeans labels");
+		}
+	}
+}
+
+namespace ml
+{
+	namespace Distributed
+	{
+		std::array<unsigned char, 128> unique_id()
+		{
+			std::array<unsigned char, 128> id{};
+			detail::check(mlb_nccl_unique_id(id.data()), "NCCL unique id");
+			return id;
+		}
+
+		void init(int device, int rank, int world, const std::array<unsigned char, 128>& id)
+		{
+			std::lock_guard<std::mutex> lock(detail::context_mutex());
+			if (detail::context_holder().ctx) {
+				throw std::logic_error("ml::Distributed::init: the process already has a GPU context (call init before the first fit)");
+			}
+			detail::check(mlb_ctx_create_rank(device, rank, world, id.data(), &detail::context_holder().ctx), "ml::Distributed::init");
+			detail::distributed_active = true;
+		}
+
+		bool active()
+		{
+			return detail::distributed_active;
+		}
+
+		std::pair<Eigen::Index, Eigen::Index> shard_range(Eigen::Index n_total, int world, int rank)
+		{
+			int64_t begin = 0, end = 0;
+			detail::check(mlb_shard_range(n_total, world, rank, &begin, &end), "ml::Distributed::shard_range");
+			return std::make_pair(static_cast<Eigen::Index>(begin), static_cast<Eigen::Index>(end));
 		}
 	}
 }

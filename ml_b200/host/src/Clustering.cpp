@@ -25,6 +25,23 @@ namespace ml
 				return m.data() + j * m.outerStride();
 			}
 
+			/** 0, 1, 2, ... as an iterator (random access only so that std::distance is O(1); std::sample walks it forwards). */
+			struct CountingIterator
+			{
+				using iterator_category = std::random_access_iterator_tag;
+				using value_type = Eigen::Index;
+				using difference_type = std::ptrdiff_t;
+				using pointer = const Eigen::Index*;
+				using reference = const Eigen::Index&;
+				Eigen::Index value;
+				reference operator*() const { return value; }
+				CountingIterator& operator++() { ++value; return *this; }
+				CountingIterator operator++(int) { CountingIterator old = *this; ++value; return old; }
+				bool operator==(const CountingIterator& other) const { return value == other.value; }
+				bool operator!=(const CountingIterator& other) const { return value != other.value; }
+				difference_type operator-(const CountingIterator& other) const { return value - other.value; }
+			};
+
 			inline double squared_distance(const double* a, const double* b, Eigen::Index dim)
 			{
 				double total = 0;
@@ -44,12 +61,12 @@ namespace ml
 
 		void Forgy::init(DataView data, Prng& prng, const unsigned int number_components, MatrixOut centroids) const
 		{
-			// std::sample over 0..N-1 (selection sampling): the draw sequence the reference makes.
-			std::vector<Eigen::Index> population(static_cast<size_t>(data.cols()));
-			std::iota(population.begin(), population.end(), Eigen::Index(0));
+			// std::sample over 0..N-1 (selection sampling): the draw sequence the reference makes.  The population is
+			// a counting iterator instead of the reference's materialised index vector (800 MB at N = 1e8): std::sample
+			// only walks it forwards, so the draws and the chosen indices are the same.
 			std::vector<Eigen::Index> chosen;
 			chosen.reserve(number_components);
-			std::sample(population.begin(), population.end(), std::back_inserter(chosen), number_components, prng);
+			std::sample(CountingIterator{0}, CountingIterator{data.cols()}, std::back_inserter(chosen), number_components, prng);
 			for (unsigned int k = 0; k < number_components; ++k) {
 				std::copy_n(point(data, chosen[k]), data.rows(), column(centroids, k));
 			}
@@ -94,6 +111,21 @@ namespace ml
 				std::discrete_distribution<Eigen::Index> draw(weights.begin(), weights.end());
 				const Eigen::Index index = draw(prng);
 				std::copy_n(point(data, index), dim, column(centroids, k));
+			}
+		}
+
+		ExplicitCentroids::ExplicitCentroids(Eigen::MatrixXd centroids)
+			: centroids_(std::move(centroids))
+		{
+		}
+
+		void ExplicitCentroids::init(DataView data, Prng&, const unsigned int number_components, MatrixOut centroids) const
+		{
+			if (centroids_.rows() != data.rows() || centroids_.cols() != static_cast<Eigen::Index>(number_components)) {
+				throw std::invalid_argument("ExplicitCentroids: stored centroids have the wrong shape");
+			}
+			for (unsigned int k = 0; k < number_components; ++k) {
+				std::copy_n(centroids_.data() + static_cast<Eigen::Index>(k) * centroids_.rows(), centroids_.rows(), column(centroids, k));
 			}
 		}
 

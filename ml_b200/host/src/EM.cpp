@@ -23,6 +23,8 @@ namespace ml
 		, covariances_(number_components)
 		, inverse_covariances_(number_components)
 		, sqrt_covariance_determinants_(number_components)
+		, labels_on_host_(true)
+		, sample_size_(0)
 		, absolute_tolerance_(1e-8)
 		, relative_tolerance_(1e-8)
 		, log_likelihood_(0)
@@ -104,6 +106,18 @@ namespace ml
 		return responsibilities_;
 	}
 
+	const std::vector<unsigned int>& EM::labels() const
+	{
+		if (!labels_on_host_ && device_) {
+			device_->emit(nullptr, &labels_);   // calculate_labels (EM.cpp:289-304) at the parameters of the last E-step
+			labels_on_host_ = true;
+		}
+		if (static_cast<Eigen::Index>(labels_.size()) != sample_size_) {
+			labels_.resize(static_cast<size_t>(sample_size_));   // EM.cpp:104; filled only by a converged fit
+		}
+		return labels_;
+	}
+
 	bool EM::fit(const DataView data)
 	{
 		converged_ = false;
@@ -120,13 +134,16 @@ namespace ml
 		device_.reset();
 		means_.resize(number_dimensions, number_components_);
 		mixing_probabilities_.fill(1. / static_cast<double>(number_components_));
-		labels_.resize(sample_size);
+		labels_.clear();
+		labels_on_host_ = true;
+		sample_size_ = sample_size;
 		responsibilities_.resize(0, 0);
 		responsibilities_on_host_ = true;
 
 		if (sample_size == number_components_) {
 			// One component per point: exact fit, nothing to iterate (EM.cpp:108-118).
 			responsibilities_ = Eigen::MatrixXd::Identity(sample_size, sample_size);
+			labels_.resize(sample_size);
 			for (unsigned int i = 0; i < sample_size; ++i) {
 				std::copy_n(data.data() + static_cast<Eigen::Index>(i) * data.outerStride(), number_dimensions, means_.data() + static_cast<Eigen::Index>(i) * number_dimensions);
 				covariances_[i].setZero(number_dimensions, number_dimensions);
@@ -198,7 +215,7 @@ namespace ml
 			if (step > 0) {
 				const double ll_change = std::abs(log_likelihood_ - old_log_likelihood);
 				if (ll_change < absolute_tolerance_ + relative_tolerance_ * std::max(std::abs(old_log_likelihood), std::abs(log_likelihood_))) {
-					device_->emit(nullptr, &labels_);   // calculate_labels (EM.cpp:289-304)
+					labels_on_host_ = false;   // calculate_labels (EM.cpp:289-304) runs on first access to labels()
 					converged_ = true;
 					break;
 				}

@@ -16,7 +16,8 @@ namespace ml
 	namespace Clustering
 	{
 		KMeans::KMeans(unsigned int number_clusters)
-			: centroids_initialiser_(std::make_shared<Forgy>())
+			: labels_on_host_(true)
+			, centroids_initialiser_(std::make_shared<Forgy>())
 			, absolute_tolerance_(1e-8)
 			, inertia_(0)
 			, maximum_steps_(1000)
@@ -27,11 +28,20 @@ namespace ml
 			, converged_(false)
 		{
 			if (!number_clusters) {
-				throw std::invalid_argument("KMeans: number of clusters must be positive");
+				throw std::invalid_argument("KMeans: number of clusters cannot be zero");
 			}
 		}
 
 		KMeans::~KMeans() = default;
+
+		const std::vector<unsigned int>& KMeans::labels() const
+		{
+			if (!labels_on_host_ && device_) {
+				device_->get_labels(labels_);
+				labels_on_host_ = true;
+			}
+			return labels_;
+		}
 
 		bool KMeans::fit(DataView data)
 		{
@@ -47,10 +57,12 @@ namespace ml
 			number_iterations_ = 0;
 			device_.reset();
 			centroids_.resize(number_dimensions, number_clusters_);
-			labels_.resize(sample_size);
+			labels_.clear();
+			labels_on_host_ = true;
 
 			if (sample_size == number_clusters_) {
 				// Every point is its own cluster (KMeans.cpp:67-75); identical for every initialisation.
+				labels_.resize(sample_size);
 				for (unsigned int i = 0; i < sample_size; ++i) {
 					std::copy_n(data.data() + static_cast<Eigen::Index>(i) * data.outerStride(), number_dimensions, centroids_.data() + static_cast<Eigen::Index>(i) * number_dimensions);
 					labels_[i] = i;
@@ -86,7 +98,7 @@ namespace ml
 					inertia_ = device.assign(changed);
 				}
 			}
-			device.get_labels(labels_);
+			labels_on_host_ = false;   // downloaded on first access to labels()
 			return converged_;
 		}
 

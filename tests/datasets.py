@@ -47,3 +47,19 @@ def synthetic_gmm(n, d, k, seed=0, spread=10.0):
         m = labels == c
         data[m] = means[c] + z[m] @ chols[c].T
     return np.ascontiguousarray(data), labels.astype(np.uint32), means
+
+
+def separated_clusters(n, d, k, separation, offset=0.0, seed=0):
+    """K unit-variance Gaussian clusters whose centres lie `separation` standard deviations apart along a line through
+    the D-cube's diagonal, all shifted by `offset` in every coordinate: the regime of un-standardised features, where the
+    distance of a component from the centre of the data, measured in its own standard deviations, is large.  Returns
+    (data (N, D), true labels, centres (K, D))."""
+    rng = np.random.default_rng(seed)
+    direction = np.ones(d) / np.sqrt(d)
+    centres = np.array([(j - (k - 1) / 2.0) * separation * direction for j in range(k)])
+    centres += rng.uniform(-0.25, 0.25, size=(k, d)) * separation   # not collinear
+    centres += offset
+    labels = rng.integers(0, k, size=n)
+    scales = rng.uniform(0.7, 1.4, size=(k, d))
+    data = centres[labels] + rng.standard_normal((n, d)) * scales[labels]
+    return np.ascontiguousarray(data), labels.astype(np.uint32), centres

@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/.."
 mkdir -p build/variants/$name
-for f in context seeding em kmeans; do
+for f in context seeding em kmeans selftest; do
   /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC "$@" \
       -c ml_b200/csrc/$f.cu -o build/variants/$name/$f.o &
 done
