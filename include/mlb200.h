@@ -122,6 +122,12 @@ int mlb_data_download(mlb_data* data, int64_t begin, int64_t count, double* out)
 int mlb_data_shape(const mlb_data* data, int64_t* n_total, int64_t* n_local, int* d);
 int mlb_data_free(mlb_data* data);
 
+/* standardise_features of the reference's Python package (cppyml/cppyml/utils.py:8-28) on the first local GPU: every
+ * dimension minus its mean and, when n > 1, divided by its BIASED standard deviation (a zero deviation divides by zero,
+ * as numpy does).  x and out are column-major D x n (a point per column) with outer strides ld, ld_out >= d; they may
+ * be the same buffer.  Sums are pairwise trees in a fixed order (numpy's accuracy, bitwise reproducible). */
+int mlb_standardise_features(mlb_ctx* ctx, const double* x, int64_t n, int d, int64_t ld, double* out, int64_t ld_out);
+
 /* ---------------------------------------------------------------- initialisers (ML/Clustering.cpp) */
 
 /* The distance pass of KPP::init (Clustering.cpp:42-51), kept incrementally: a per-point vector `nearest`
@@ -139,6 +145,7 @@ int mlb_data_launch_count(const mlb_data* data, int64_t* launches);
 
 /* ---------------------------------------------------------------- Gaussian-mixture EM (ML/EM.cpp) */
 
+/* Any K >= 1; D <= 128 (MLB_EINVAL beyond: the parameter refresh factorises a D x D covariance inside one SM). */
 int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out);
 int mlb_em_destroy(mlb_em* em);
 
@@ -200,14 +207,28 @@ int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double*
 int mlb_em_set_kernel_timing(mlb_em* em, int enabled);
 int mlb_em_kernel_time_ms(mlb_em* em, double* total_ms, int64_t* launches);
 
-/* Which device path the last step used: 1 = fused DMMA E+M kernel, 2 = split E / M kernels. */
+/* Which device path the last step used: 1 = fused DMMA E+M kernel, 2 = split E / M kernels (both in feature space
+ * about the data mean), 3 = direct-difference E / M kernels (per-component centring, as EM.cpp:205-207,246-248). */
 int mlb_em_last_path(const mlb_em* em, int* path);
+
+/* Numerical domain of the feature-space kernels and the routing between the paths.  The feature-space kernels expand
+ * the quadratic form about ONE shift c (the data mean); their error grows with kappa = max_k (mu_k - c)^T P_k (mu_k - c),
+ * the squared distance of a component from the centre of the data in its own standard deviations (relative error
+ * ~1e-16 kappa: 1e-13 for standardised data, 1e-8 for tight clusters 1e4 standard deviations apart).  The library
+ * computes kappa with every parameter refresh and runs the next step on the direct-difference kernels whenever
+ * kappa > 3e4, when D > 64 or K > 256 (shapes only those kernels take), or when forced.  Guaranteed domain: results
+ * within 1e-9 of the reference wherever the reference itself is finite, for any K and D <= 128.
+ * mlb_em_force_path: path = 3 always uses the direct kernels, 0 restores the automatic choice.
+ * mlb_em_conditioning: kappa of the current parameters and the path the next step will take. */
+int mlb_em_force_path(mlb_em* em, int path);
+int mlb_em_conditioning(mlb_em* em, double* kappa_max, int* next_path);
 /* Number of kernels the library launched on this object since creation (bench "gpu_launches"). */
 int mlb_em_launch_count(const mlb_em* em, int64_t* launches);
 
 /* ---------------------------------------------------------------- K-means (ML/KMeans.cpp) */
 
-/* D <= 64; any K (centroids that do not fit one CTA's shared memory are processed in blocks, same results). */
+/* D <= 128 (MLB_EINVAL beyond); any K (centroids that do not fit one CTA's shared memory are processed in blocks, same
+ * results).  D <= 64 runs the DMMA filter + exact refinement, wider points the reference's scan as written. */
 int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out);
 int mlb_km_destroy(mlb_km* km);
 

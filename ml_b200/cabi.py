@@ -10,6 +10,7 @@ as C-contiguous (K, D) arrays (the same memory).
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 
@@ -49,6 +50,7 @@ SIGNATURES = {
     "mlb_data_download": (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64, _vp]),
     "mlb_data_shape": (ctypes.c_int, [_vp, _c_i64p, _c_i64p, _c_ip]),
     "mlb_data_free": (ctypes.c_int, [_vp]),
+    "mlb_standardise_features": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, _vp, ctypes.c_int64]),
     "mlb_data_kpp_update": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp]),
     "mlb_data_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
     "mlb_em_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
@@ -67,6 +69,8 @@ SIGNATURES = {
     "mlb_em_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "mlb_em_kernel_time_ms": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
     "mlb_em_last_path": (ctypes.c_int, [_vp, _c_ip]),
+    "mlb_em_force_path": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "mlb_em_conditioning": (ctypes.c_int, [_vp, _c_dp, _c_ip]),
     "mlb_em_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
     "mlb_km_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.POINTER(_vp)]),
     "mlb_km_destroy": (ctypes.c_int, [_vp]),
@@ -135,6 +139,16 @@ def fp64_peak(device=0):
     return a.value, b.value
 
 
+def standardise_features(ctx, features):
+    """cppyml.utils.standardise_features (cppyml/cppyml/utils.py:8-28) on the device: (N, D) -> standardised copy."""
+    x = np.ascontiguousarray(features, dtype=np.float64)
+    assert x.ndim == 2
+    out = np.empty_like(x)
+    if x.size:
+        check(lib().mlb_standardise_features(ctx._h, _ptr(x), x.shape[0], x.shape[1], x.shape[1], _ptr(out), x.shape[1]))
+    return out
+
+
 def shard_range(n_total, world, rank):
     b, e = ctypes.c_int64(), ctypes.c_int64()
     check(lib().mlb_shard_range(n_total, world, rank, ctypes.byref(b), ctypes.byref(e)))
@@ -153,6 +167,7 @@ class Context:
 
     def __init__(self, n_devices=1, devices=None, _handle=None):
         self._h = _vp()
+        self._children = weakref.WeakSet()   # Data / Em / Km objects living on this context: closed before it is
         if _handle is not None:
             self._h = _handle
             return
@@ -188,6 +203,12 @@ class Context:
 
     def close(self):
         if self._h:
+            # objects that outlived their scope (a test that failed before its own close()) must go first: their handles
+            # point into this context
+            for kind in (Em, Km, Data):
+                for child in list(self._children):
+                    if isinstance(child, kind):
+                        child.close()
             lib().mlb_ctx_destroy(self._h)
             self._h = _vp()
 
@@ -205,6 +226,7 @@ class Data:
         self.ctx = ctx
         self._h = handle
         self._keep = keep
+        ctx._children.add(self)
 
     @classmethod
     def upload(cls, ctx, points, n_total=None):
@@ -280,6 +302,7 @@ class Em:
         self.n_total, self.n_local, self.d = data.shape
         self._h = _vp()
         check(lib().mlb_em_create(data.ctx._h, data._h, k, ctypes.byref(self._h)))
+        data.ctx._children.add(self)
 
     def sample_covariance(self):
         cov = np.empty((self.d, self.d))
@@ -373,6 +396,16 @@ class Em:
         check(lib().mlb_em_last_path(self._h, ctypes.byref(p)))
         return p.value
 
+    def force_path(self, path):
+        """3: always the direct-difference kernels; 0: automatic routing."""
+        check(lib().mlb_em_force_path(self._h, path))
+
+    def conditioning(self):
+        """(kappa of the current parameters, path of the next step)."""
+        kappa, path = ctypes.c_double(), ctypes.c_int()
+        check(lib().mlb_em_conditioning(self._h, ctypes.byref(kappa), ctypes.byref(path)))
+        return kappa.value, path.value
+
     @property
     def launch_count(self):
         c = ctypes.c_int64()
@@ -400,6 +433,7 @@ class Km:
         self.n_total, self.n_local, self.d = data.shape
         self._h = _vp()
         check(lib().mlb_km_create(data.ctx._h, data._h, k, ctypes.byref(self._h)))
+        data.ctx._children.add(self)
 
     def set_centroids(self, centroids_dk):
         c = np.ascontiguousarray(np.asarray(centroids_dk, dtype=np.float64).T)

@@ -94,7 +94,7 @@ static int copy_threads(size_t bytes)
 {
     if (bytes < kThreadedCopyBytes) return 1;
     const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
-    int t = static_cast<int>(std::min<unsigned>(kCopyThreadsMax, std::max(2u, cores / (2u * static_cast<unsigned>(g_ranks_on_host)))));
+    int t = static_cast<int>(std::min<unsigned>(kCopyThreadsMax, std::max(2u, g_ranks_on_host > 1 ? cores / static_cast<unsigned>(g_ranks_on_host) : cores / 2u)));
     if (const char* env = std::getenv("MLB200_COPY_THREADS")) t = std::max(1, std::min(kCopyThreadsMax, std::atoi(env)));
     return t;
 }
@@ -164,43 +164,55 @@ int staged_h2d(Gpu& gpu, void* dst_device, const void* src, size_t rows, size_t 
     });
 }
 
-int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes)
+int staged_d2h_2d(Gpu& gpu, void* dst, size_t dst_stride, const void* src_device, size_t src_stride, size_t rows, size_t row_bytes)
 {
-    if (bytes == 0) return MLB_OK;
+    const size_t total = rows * row_bytes;
+    if (total == 0) return MLB_OK;
     if (is_pinned_host(dst)) {
-        MLB_CUDA(cudaMemcpyAsync(dst, src_device, bytes, cudaMemcpyDeviceToHost, gpu.stream));
+        if (rows == 1) MLB_CUDA(cudaMemcpyAsync(dst, src_device, row_bytes, cudaMemcpyDeviceToHost, gpu.stream));
+        else MLB_CUDA(cudaMemcpy2DAsync(dst, dst_stride, src_device, src_stride, row_bytes, rows, cudaMemcpyDeviceToHost, gpu.stream));
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
         return MLB_OK;
     }
     MLB_TRY(ensure_bounce(gpu));
-    const size_t pieces = (bytes + kBounceBytes - 1) / kBounceBytes;
-    const int threads = static_cast<int>(std::min<size_t>(copy_threads(bytes), pieces));
+    // pieces of at most kBounceBytes that never straddle a row
+    const size_t per_row = (row_bytes + kBounceBytes - 1) / kBounceBytes;
+    const size_t pieces = rows * per_row;
+    const int threads = static_cast<int>(std::min<size_t>(copy_threads(total), pieces));
     char* out = static_cast<char*>(dst);
     const char* in = static_cast<const char*>(src_device);
     return run_copy_threads(threads, [&](int t) -> int {
         MLB_CUDA(cudaSetDevice(gpu.device));
-        // two buffers per thread: the DMA of this thread's next piece runs while it copies the previous one out
-        size_t prev_off = 0, prev_len = 0;
+        // two buffers per thread: the DMA of this thread's next piece runs while it copies the previous one out (the
+        // destination is usually fresh memory, so this copy is where its pages are first touched: that, spread over the
+        // threads, is what bounds a large download)
+        char* prev_dst = nullptr;
+        size_t prev_len = 0;
         int turn = 0;
         for (size_t piece = static_cast<size_t>(t); piece < pieces; piece += static_cast<size_t>(threads), ++turn) {
             const int slot = 2 * t + (turn & 1);
-            const size_t off = piece * kBounceBytes, len = std::min(kBounceBytes, bytes - off);
-            MLB_CUDA(cudaMemcpyAsync(gpu.bounce[slot], in + off, len, cudaMemcpyDeviceToHost, gpu.stream));
+            const size_t row = piece / per_row, off = (piece - row * per_row) * kBounceBytes, len = std::min(kBounceBytes, row_bytes - off);
+            MLB_CUDA(cudaMemcpyAsync(gpu.bounce[slot], in + row * src_stride + off, len, cudaMemcpyDeviceToHost, gpu.stream));
             MLB_CUDA(cudaEventRecord(gpu.bounce_ev[slot], gpu.stream));
             if (turn > 0) {
                 MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[slot ^ 1]));
-                std::memcpy(out + prev_off, gpu.bounce[slot ^ 1], prev_len);
+                std::memcpy(prev_dst, gpu.bounce[slot ^ 1], prev_len);
             }
-            prev_off = off;
+            prev_dst = out + row * dst_stride + off;
             prev_len = len;
         }
         if (turn > 0) {
             const int last = 2 * t + ((turn - 1) & 1);
             MLB_CUDA(cudaEventSynchronize(gpu.bounce_ev[last]));
-            std::memcpy(out + prev_off, gpu.bounce[last], prev_len);
+            std::memcpy(prev_dst, gpu.bounce[last], prev_len);
         }
         return MLB_OK;
     });
+}
+
+int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes)
+{
+    return staged_d2h_2d(gpu, dst, bytes, src_device, bytes, 1, bytes);
 }
 
 int KernelTimer::begin(cudaStream_t stream)
@@ -348,26 +360,27 @@ void ReduceScratch::release(mlb_ctx* ctx)
     len.clear();
 }
 
-int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s, ReduceScratch& scratch)
+int reduce_and_exchange_units(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s, ReduceScratch& scratch,
+                              const int64_t* bounds)
 {
     mlb_ctx* ctx = data->ctx;
     const int vpg = ctx->vshards_per_gpu();
     scratch.ptr.resize(ctx->gpus.size(), nullptr);
     scratch.len.resize(ctx->gpus.size(), 0);
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
-        DataShard& sh = data->shards[g];
+        const int64_t local_begin = bounds[gpu.rank * vpg];   // partials[g] starts at the first unit of this GPU's first shard
         VshardRanges r, rg;
         int64_t total_groups = 0;
         for (int j = 0; j < vpg; ++j) {
             const int v = gpu.rank * vpg + j;
-            r.lo[j] = data->lay.vshard_chunk[v] - sh.chunk_begin;
-            r.hi[j] = data->lay.vshard_chunk[v + 1] - sh.chunk_begin;
+            r.lo[j] = bounds[v] - local_begin;
+            r.hi[j] = bounds[v + 1] - local_begin;
             rg.lo[j] = total_groups;
             total_groups += (r.hi[j] - r.lo[j] + kReduceGroup - 1) / kReduceGroup;
             rg.hi[j] = total_groups;
         }
         double* out = vsum[g] + static_cast<int64_t>(gpu.rank) * vpg * s;
-        if (data->lay.n_chunks <= 2 * kReduceGroup * kVirtualShards) {
+        if (bounds[kVirtualShards] <= 2 * kReduceGroup * kVirtualShards) {
             // few chunks: one level.  (The choice depends on N only, never on the GPU count: the two orders differ.)
             reduce_partials_kernel<<<dim3((s + 31) / 32, vpg), dim3(32, 8), 0, gpu.stream>>>(partials[g], r, s, out);
             MLB_CUDA(cudaGetLastError());
@@ -401,6 +414,11 @@ int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, co
         MLB_NCCL(api, api->GroupEnd());
     }
     return MLB_OK;
+}
+
+int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s, ReduceScratch& scratch)
+{
+    return reduce_and_exchange_units(data, partials, vsum, s, scratch, data->lay.vshard_chunk);
 }
 
 // ---------------------------------------------------------------- column sums (data mean)
@@ -466,6 +484,72 @@ static int compute_shift(mlb_data* data)
         return MLB_OK;
     }));
     return MLB_OK;
+}
+
+// ---------------------------------------------------------------- feature standardisation (cppyml/cppyml/utils.py:8-28)
+
+// Per block of rows: column sums of x (mean == nullptr) or of (x - mean)^2.  Thread t owns coordinate t % d of every
+// (blockDim / d)-th point of the block's rows, then a fixed shared-memory order: deterministic.
+__global__ void standardise_partial_kernel(const double* __restrict__ x, int64_t n, int d, int64_t rows_per_block, const double* __restrict__ mean,
+                                           double* __restrict__ partials)
+{
+    extern __shared__ double sm[];
+    const int64_t p0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+    const int64_t p1 = min(p0 + rows_per_block, n);
+    const int lanes = blockDim.x / d, t = threadIdx.x, c = t % d, lane = t / d;
+    double acc = 0;
+    if (lane < lanes) {
+        const double m = mean ? mean[c] : 0.0;
+        for (int64_t p = p0 + lane; p < p1; p += lanes) {
+            const double v = x[p * d + c] - m;
+            acc += mean ? v * v : v;
+        }
+    }
+    sm[t] = lane < lanes ? acc : 0.0;
+    __syncthreads();
+    if (t < d) {
+        double s = 0;
+        for (int l = 0; l < lanes; ++l) s += sm[l * d + t];
+        partials[static_cast<int64_t>(blockIdx.x) * d + t] = s;
+    }
+}
+
+// out[c] = f(sum over the blocks of partials[b][c]) in a fixed pairwise order; f = / n (mean) or sqrt(. / n) (biased std).
+__global__ void standardise_finish_kernel(const double* __restrict__ partials, int nblocks, int d, int64_t n, int want_std, double* __restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d) return;
+    // pairwise (tree) sum over the blocks: the accuracy of numpy's pairwise summation, in a fixed order
+    double level[32];
+    int filled = 0;   // bit i set: level[i] holds the sum of 2^i blocks
+    for (int b = 0; b < nblocks; ++b) {
+        double v = partials[static_cast<int64_t>(b) * d + c];
+        int i = 0;
+        while (filled & (1 << i)) {
+            v += level[i];
+            filled &= ~(1 << i);
+            ++i;
+        }
+        level[i] = v;
+        filled |= 1 << i;
+    }
+    double total = 0.0;
+    bool first = true;
+    for (int i = 0; i < 32; ++i)
+        if (filled & (1 << i)) {
+            total = first ? level[i] : total + level[i];
+            first = false;
+        }
+    out[c] = want_std ? sqrt(total / static_cast<double>(n)) : total / static_cast<double>(n);
+}
+
+__global__ void standardise_apply_kernel(double* __restrict__ x, int64_t total, int d, const double* __restrict__ mean, const double* __restrict__ sd, int divide)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % d);
+    const double v = x[i] - mean[c];
+    x[i] = divide ? v / sd[c] : v;
 }
 
 // ---------------------------------------------------------------- synthetic GMM generator
@@ -983,6 +1067,51 @@ int mlb_data_shape(const mlb_data* data, int64_t* n_total, int64_t* n_local, int
     }
     if (d) *d = data->d;
     return MLB_OK;
+}
+
+int mlb_standardise_features(mlb_ctx* ctx, const double* x, int64_t n, int d, int64_t ld, double* out, int64_t ld_out)
+{
+    MLB_ENTER(ctx);
+    MLB_REQUIRE(ctx && x && out, "mlb_standardise_features: null argument");
+    MLB_REQUIRE(n >= 1 && d >= 1 && d <= 1024 && ld >= d && ld_out >= d, "mlb_standardise_features: bad shape (n=%lld, d=%d)", static_cast<long long>(n), d);
+    Gpu& gpu = ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    double *xd = nullptr, *partials = nullptr, *mean = nullptr, *sd = nullptr;
+    const int threads = std::max(d, 256 / d * d);
+    const int64_t rows_per_block = 4096;
+    const int nblocks = static_cast<int>((n + rows_per_block - 1) / rows_per_block);
+    auto body = [&]() -> int {
+        MLB_CUDA(cudaMallocFromPoolAsync(&xd, sizeof(double) * n * d, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&partials, sizeof(double) * nblocks * d, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&mean, sizeof(double) * d, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&sd, sizeof(double) * d, gpu.pool, gpu.stream));
+        MLB_TRY(staged_h2d(gpu, xd, x, static_cast<size_t>(n), sizeof(double) * d, sizeof(double) * ld));
+        standardise_partial_kernel<<<nblocks, threads, sizeof(double) * threads, gpu.stream>>>(xd, n, d, rows_per_block, nullptr, partials);
+        MLB_CUDA(cudaGetLastError());
+        standardise_finish_kernel<<<(d + 127) / 128, 128, 0, gpu.stream>>>(partials, nblocks, d, n, 0, mean);
+        MLB_CUDA(cudaGetLastError());
+        if (n > 1) {   // utils.py:25-27: the division happens only with more than one row
+            standardise_partial_kernel<<<nblocks, threads, sizeof(double) * threads, gpu.stream>>>(xd, n, d, rows_per_block, mean, partials);
+            MLB_CUDA(cudaGetLastError());
+            standardise_finish_kernel<<<(d + 127) / 128, 128, 0, gpu.stream>>>(partials, nblocks, d, n, 1, sd);
+            MLB_CUDA(cudaGetLastError());
+        }
+        const int64_t total = n * d;
+        standardise_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, gpu.stream>>>(xd, total, d, mean, sd, n > 1 ? 1 : 0);
+        MLB_CUDA(cudaGetLastError());
+        if (ld_out == d) {
+            MLB_TRY(staged_d2h(gpu, out, xd, sizeof(double) * total));
+        } else {
+            MLB_TRY(staged_d2h_2d(gpu, out, sizeof(double) * ld_out, xd, sizeof(double) * d, static_cast<size_t>(n), sizeof(double) * d));
+        }
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    };
+    const int rc = body();
+    cudaStreamSynchronize(gpu.stream);
+    for (double* ptr : {xd, partials, mean, sd})
+        if (ptr) cudaFreeAsync(ptr, gpu.stream);
+    return rc;
 }
 
 }  // extern "C"

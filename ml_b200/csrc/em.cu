@@ -24,6 +24,7 @@
 #include <cstring>
 #include <limits>
 
+#include "em_direct.cuh"
 #include "em_split.cuh"
 #include "fastmath.cuh"
 #include "internal.h"
@@ -391,9 +392,11 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? ML
 // Stage 2: process_covariances (EM.cpp:274-287): Cholesky, inverse by solving against the identity,
 // sqrt|Sigma| = prod L_ii; then the E-step image theta for the next iteration.
 struct EmFinalizeArgs {
-    const double* vsum;   // [8][SV] or nullptr
+    const double* vsum;   // feature-path statistics [8][SV] (moments about the shift c), or nullptr
+    const double* dstats; // direct-path statistics [8][dSV] (augmented moments about each component's old mean), or nullptr
     const double* shift;
     int d, k, DP, KP, SV;
+    int DPd, dSV;         // direct path: D padded to 8, length of a statistics vector
     long long n_total;
     const int2* feat_m;   // [NM*8]
     const int2* feat_e;   // [NE*4]: (a, b); b == DP: linear term a; a < 0: unused slot
@@ -403,7 +406,10 @@ struct EmFinalizeArgs {
     double* weights;      // K
     double* inv_covs;     // K x (D x D)
     double* sqrt_dets;    // K
-    double* theta_out;    // E-step image
+    double* theta_out;    // E-step image of the feature kernels, or nullptr (shapes only the direct kernels take)
+    double* dimg_out;     // E-step images of the direct kernels [k][dr_img_len(DPd)], or nullptr
+    double* kappa_out;    // [k] delta^T P delta: how far (in its own standard deviations, squared) a component sits from the shift
+    int p_in_smem;        // the inverse covariance fits next to the factor in shared memory
     double* ll_ring;      // ring of log-likelihoods of the E-steps whose statistics these are (nullptr: skip)
     unsigned long long* ll_counter;   // device-side step counter: the ring slot written is *ll_counter % ring, then it is incremented
     int ll_ring_len;
@@ -413,14 +419,14 @@ __global__ void em_finalize_kernel(const EmFinalizeArgs p)
 {
     extern __shared__ double fs[];
     const int d = p.d, DP = p.DP, KP = p.KP, NT = KP / 8;
-    double* A = fs;            // covariance, column-major d x d
-    double* L = A + d * d;     // Cholesky factor (lower)
-    double* P = L + d * d;     // inverse covariance
-    double* delta = P + d * d; // mean - shift
+    double* A = fs;            // covariance, column-major d x d, factorised in place
+    double* L = A;             // Cholesky factor (lower)
+    double* delta = A + d * d; // mean - shift
     double* m1 = delta + d;
     double* v = m1 + d;        // P delta
-    __shared__ double s_count, s_const;
     const int kc = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    double* P = p.p_in_smem ? v + d : p.inv_covs + static_cast<long long>(kc < p.k ? kc : 0) * d * d;   // inverse covariance
+    __shared__ double s_count, s_const;
     const bool real = kc < p.k;
     double weight = 0.0;
 
@@ -447,15 +453,46 @@ __global__ void em_finalize_kernel(const EmFinalizeArgs p)
             weight = s / static_cast<double>(p.n_total);
             for (int a = tid; a < d; a += nthr) p.means[a + kc * d] = p.shift[a] + delta[a];
             if (tid == 0) p.weights[kc] = weight;
+        } else if (p.dstats) {
+            // Moments about the component's own previous mean (em_direct.cuh): s, m1 = sum r w, m2 = sum r w w^T with
+            // w = x - mu_old.  mu_new = mu_old + m1/s, Sigma = m2/s - (m1/s)(m1/s)^T + 1e-15 I (EM.cpp:238-257).
+            const int NBa = p.DPd / 8 + 1, NB = NBa - 1;
+            const double* st = p.dstats + static_cast<long long>(kc) * dr_stat_len(p.DPd);
+            if (tid == 0) s_count = tree8(st + dr_tile_index(NBa, NB, NB) * 64, p.dSV);
+            for (int a = tid; a < d; a += nthr) m1[a] = tree8(st + dr_tile_index(NBa, a / 8, NB) * 64 + (a % 8) * 8, p.dSV);
+            for (int e = tid; e < d * d; e += nthr) {
+                const int a = e % d, b = e / d;
+                if (a <= b) {   // the tile entry (a, b) only: (r w_a) w_b and (r w_b) w_a round differently
+                    const double val = tree8(st + dr_tile_index(NBa, a / 8, b / 8) * 64 + (a % 8) * 8 + (b % 8), p.dSV);
+                    A[a + b * d] = val;
+                    A[b + a * d] = val;
+                }
+            }
+            __syncthreads();
+            const double s = s_count;
+            for (int a = tid; a < d; a += nthr) m1[a] = m1[a] / s;
+            __syncthreads();
+            for (int e = tid; e < d * d; e += nthr) {
+                const int a = e % d, b = e / d;
+                double cv = A[e] / s - m1[a] * m1[b];
+                if (a == b) cv += 1e-15;
+                A[e] = cv;
+                p.covs[static_cast<long long>(kc) * d * d + e] = cv;
+            }
+            weight = s / static_cast<double>(p.n_total);
+            for (int a = tid; a < d; a += nthr) {
+                const double mean = p.means[a + kc * d] + m1[a];
+                p.means[a + kc * d] = mean;
+                delta[a] = mean - p.shift[a];
+            }
+            if (tid == 0) p.weights[kc] = weight;
         } else {
             for (int e = tid; e < d * d; e += nthr) A[e] = p.covs[static_cast<long long>(kc) * d * d + e];
             for (int a = tid; a < d; a += nthr) delta[a] = p.means[a + kc * d] - p.shift[a];
             weight = p.weights[kc];
         }
         __syncthreads();
-        // Unblocked left-looking Cholesky, sequential inner sums (same order as the oracle's restatement of Eigen::LLT).
-        for (int e = tid; e < d * d; e += nthr) L[e] = A[e];
-        __syncthreads();
+        // Unblocked left-looking Cholesky in place, sequential inner sums (same order as the oracle's restatement of Eigen::LLT).
         for (int j = 0; j < d; ++j) {
             if (tid == 0) {
                 double x = L[j + j * d];
@@ -475,7 +512,7 @@ __global__ void em_finalize_kernel(const EmFinalizeArgs p)
             }
             __syncthreads();
         }
-        // llt.solve(Identity): forward then backward substitution, one column per thread.
+        // llt.solve(Identity): forward then backward substitution, one column per thread (only the lower triangle of L is read).
         for (int col = tid; col < d; col += nthr) {
             double* x = P + col * d;
             for (int i = 0; i < d; ++i) x[i] = i == col ? 1.0 : 0.0;
@@ -491,7 +528,8 @@ __global__ void em_finalize_kernel(const EmFinalizeArgs p)
             }
         }
         __syncthreads();
-        for (int e = tid; e < d * d; e += nthr) p.inv_covs[static_cast<long long>(kc) * d * d + e] = P[e];
+        if (p.p_in_smem)
+            for (int e = tid; e < d * d; e += nthr) p.inv_covs[static_cast<long long>(kc) * d * d + e] = P[e];
         // v = P_sym delta using the upper triangle only, as xAx_symmetric does (LinearAlgebra.cpp:17-29)
         for (int a = tid; a < d; a += nthr) {
             double acc = 0.0;
@@ -506,26 +544,50 @@ __global__ void em_finalize_kernel(const EmFinalizeArgs p)
             double dv = 0.0;
             for (int a = 0; a < d; ++a) dv += delta[a] * v[a];
             s_const = log(weight / sqrt_det) - 0.5 * dv;
+            if (p.kappa_out) p.kappa_out[kc] = dv;
+            if (p.dimg_out) p.dimg_out[static_cast<long long>(kc) * dr_img_len(p.DPd) + dr_steps(p.DPd / 8) * 32 + p.DPd] = log(weight / sqrt_det);
         }
         __syncthreads();
-    }
-    // E-step image
-    const int nt = kc / 8, row = kc % 8;
-    for (int idx = tid; idx < p.ne * 4; idx += nthr) {
-        const int j = idx >> 2, c = idx & 3;
-        const int2 ab = p.feat_e[idx];
-        double val = 0.0;
-        if (real && ab.x >= 0 && ab.x < d) {
-            if (ab.y == DP) val = v[ab.x];
-            else if (ab.y < d) val = ab.x == ab.y ? -0.5 * P[ab.x + ab.x * d] : -P[ab.x + ab.y * d];
+        if (p.dimg_out) {
+            // Direct-kernel image: the DMMA steps of P' (block upper triangle; 2 P above the diagonal blocks), then delta.
+            const int NB = p.DPd / 8, SPC = dr_steps(NB);
+            double* im = p.dimg_out + static_cast<long long>(kc) * dr_img_len(p.DPd);
+            for (int idx = tid; idx < SPC * 32; idx += nthr) {
+                const int step = idx >> 5, lane = idx & 31, g = lane >> 2, c = lane & 3;
+                int B = 0;
+                while ((B + 1) * (B + 2) <= step) ++B;        // steps before block column B: B (B + 1)
+                const int s2 = step - B * (B + 1);
+                const int a = 4 * s2 + c, n = 8 * B + g;
+                double val = 0.0;
+                if (a < d && n < d) {
+                    val = a <= n ? P[a + n * d] : P[n + a * d];
+                    if (a / 8 != B) val *= 2.0;
+                }
+                im[idx] = val;
+            }
+            for (int a = tid; a < p.DPd; a += nthr) im[SPC * 32 + a] = a < d ? delta[a] : 0.0;
+            if (tid >= 1 && tid < 8) im[SPC * 32 + p.DPd + tid] = 0.0;
         }
-        const int lane = row * 4 + c;
-        if (NT == 1) p.theta_out[j * 32 + lane] = val;
-        else p.theta_out[((j * (NT / 2) + nt / 2) * 32 + lane) * 2 + (nt & 1)] = val;
     }
-    if (tid == 0) p.theta_out[p.ne * NT * 32 + kc] = real ? s_const : -INFINITY;
-    if (p.ll_ring && p.vsum && kc == 0 && tid == 0) {
-        const double ll_sum = tree8(p.vsum + (p.SV - 8), p.SV);
+    // E-step image of the feature kernels
+    if (p.theta_out) {
+        const int nt = kc / 8, row = kc % 8;
+        for (int idx = tid; idx < p.ne * 4; idx += nthr) {
+            const int j = idx >> 2, c = idx & 3;
+            const int2 ab = p.feat_e[idx];
+            double val = 0.0;
+            if (real && ab.x >= 0 && ab.x < d) {
+                if (ab.y == DP) val = v[ab.x];
+                else if (ab.y < d) val = ab.x == ab.y ? -0.5 * P[ab.x + ab.x * d] : -P[ab.x + ab.y * d];
+            }
+            const int lane = row * 4 + c;
+            if (NT == 1) p.theta_out[j * 32 + lane] = val;
+            else p.theta_out[((j * (NT / 2) + nt / 2) * 32 + lane) * 2 + (nt & 1)] = val;
+        }
+        if (tid == 0 && kc < KP) p.theta_out[p.ne * NT * 32 + kc] = real ? s_const : -INFINITY;
+    }
+    if (p.ll_ring && (p.vsum || p.dstats) && kc == 0 && tid == 0) {
+        const double ll_sum = p.vsum ? tree8(p.vsum + (p.SV - 8), p.SV) : tree8(p.dstats + (p.dSV - 8), p.dSV);
         // mean over points minus D log(2 pi) / 2 (EM.cpp:197-211).  The slot comes from a device-side counter so that
         // the launch arguments are the same for every step (the step is replayed from a CUDA graph).
         const unsigned long long idx = *p.ll_counter;
@@ -583,6 +645,38 @@ struct EmGpu {
 
 using EmSplitKernelFn = void (*)(EmSplitArgs);
 
+// Direct-difference kernels (em_direct.cuh): per-GPU buffers.  The image and kappa are small and always present; the
+// responsibilities, the super-chunk partials and the tables are allocated when the path is first taken.
+struct EmDirectGpu {
+    double* img = nullptr;        // [k][IMG] component images
+    double* kappa = nullptr;      // [k] delta^T P delta of the current parameters
+    double* r = nullptr;          // [n_local][KPr]
+    double* ll_tile = nullptr;    // [ceil(n_local / 64)]
+    double* partials = nullptr;   // [n_sc][SVd]
+    double* vsum = nullptr;       // [8][SVd]
+    long long* sc_begin = nullptr;   // [n_sc + 1]
+    int2* tile_tab = nullptr;     // [T]
+    int n_sc = 0;
+    int grid_e = 0, grid_m = 0;
+};
+
+struct EmDirect {
+    bool capable = false;         // D <= 128
+    bool ready = false;           // the large buffers exist
+    int DP = 0, NB = 0, KPr = 0, IMG = 0, L = 0, SVd = 0;
+    int cb = 1, cg = 1, tiles_per_range = 0, n_ranges = 1;
+    size_t smem_e = 0, smem_m = 0;
+    int64_t sc_bounds[kVirtualShards + 1] = {};   // global super-chunk boundaries of the virtual shards
+    std::vector<EmDirectGpu> gpus;
+    ReduceScratch scratch;
+};
+
+constexpr int kDirectMaxDim = 128;
+// Above this kappa = max_k (mu_k - c)^T P_k (mu_k - c) the feature-space kernels lose more than ~1e-11 to cancellation
+// (measured: kappa = 2e6 still agrees with the reference to 1e-10, kappa = 2e8 to 2e-8; tests/test_gpu_numerical_domain.py)
+// and the step is routed to the direct kernels.
+constexpr double kKappaDirect = 3.0e4;
+
 constexpr int kLlRing = 4096;
 constexpr long long kStagePoints = 1 << 20;
 
@@ -602,7 +696,13 @@ struct mlb_em {
     int64_t launches = 0;
     int64_t steps_done = 0;
     EmKernelFn fn_step = nullptr, fn_mstep = nullptr, fn_emit = nullptr;
-    int path = 1;                // 1: fused E+M kernel (D <= 16, K <= 32); 2: split E / M kernels
+    int path = 1;                // feature-space kernels of this shape: 1 fused E+M (D <= 16, K <= 32), 2 split E / M; 0: none (D > 64 or K > 256)
+    EmDirect dr;                 // direct-difference kernels
+    int forced_path = 0;         // mlb_em_force_path: 0 automatic, 3 always direct
+    int route = 1;               // the path the NEXT step takes with the current parameters: `path`, or 3 (direct)
+    double kappa_max = 0.0;      // max_k (mu_k - c)^T P_k (mu_k - c) of the current parameters
+    bool r_direct_valid = false; // the direct R buffer holds the responsibilities of the last step
+    double* kappa_host = nullptr;   // pinned: kappa of the current parameters on its way to the routing decision
     EmSplitKernelFn fn_split_e = nullptr, fn_split_m = nullptr;
     size_t smem_split_e = 0, smem_split_m = 0;
     size_t smem_fused = 0;       // dynamic shared memory of the fused kernels (em_small_kernel for D <= 8, em_kernel for D = 16)
@@ -723,11 +823,12 @@ static int launch_pass(mlb_em* em, int g, const double* theta, bool timed)
     return launch_em(em, em->fn_step, a, g, em->gpus[g].grid);
 }
 
-static EmFinalizeArgs finalize_args(const mlb_em* em, int g, bool from_stats, int theta_slot, bool want_ll)
+// stats: 0 = parameters as they are (set_params), 1 = feature-path statistics, 2 = direct-path statistics
+static EmFinalizeArgs finalize_args(const mlb_em* em, int g, int stats, int theta_slot, bool want_ll)
 {
     const EmGpu& eg = em->gpus[g];
     EmFinalizeArgs f{};
-    f.vsum = from_stats ? eg.vsum : nullptr;
+    f.vsum = stats == 1 ? eg.vsum : nullptr;
     f.shift = em->data->shards[g].shift;
     f.d = em->d; f.k = em->k; f.DP = em->DP; f.KP = em->KP; f.SV = em->SV;
     f.n_total = em->data->lay.n_total;
@@ -735,20 +836,225 @@ static EmFinalizeArgs finalize_args(const mlb_em* em, int g, bool from_stats, in
     f.nm8 = em->NM * 8; f.ne = em->NE;
     f.means = em->means(g); f.covs = em->covs(g); f.weights = em->weights(g);
     f.inv_covs = em->inv_covs(g); f.sqrt_dets = em->sqrt_dets(g);
-    f.theta_out = eg.theta[theta_slot];
+    f.theta_out = em->path ? eg.theta[theta_slot] : nullptr;
+    if (em->dr.capable) {
+        const EmDirectGpu& dg = em->dr.gpus[g];
+        f.DPd = em->dr.DP; f.dSV = em->dr.SVd;
+        f.dstats = stats == 2 ? dg.vsum : nullptr;
+        f.dimg_out = dg.img;
+        f.kappa_out = dg.kappa;
+    }
     f.ll_ring = want_ll ? eg.ll : nullptr;
     f.ll_counter = eg.ll_counter;
     f.ll_ring_len = kLlRing;
     return f;
 }
 
-static int launch_finalize(mlb_em* em, int g, bool from_stats, int theta_slot, bool want_ll)
+static size_t finalize_smem(const mlb_em* em, bool* p_in_smem)
 {
-    const EmFinalizeArgs f = finalize_args(em, g, from_stats, theta_slot, want_ll);
-    const size_t smem = sizeof(double) * (3 * em->d * em->d + 3 * em->d);
-    em_finalize_kernel<<<em->KP, 128, smem, em->ctx->gpus[g].stream>>>(f);
+    const size_t d = static_cast<size_t>(em->d);
+    const size_t with_p = sizeof(double) * (2 * d * d + 3 * d), without = sizeof(double) * (d * d + 3 * d);
+    const bool fits = with_p <= 200 * 1024;
+    if (p_in_smem) *p_in_smem = fits;
+    return fits ? with_p : without;
+}
+
+static int launch_finalize(mlb_em* em, int g, int stats, int theta_slot, bool want_ll)
+{
+    EmFinalizeArgs f = finalize_args(em, g, stats, theta_slot, want_ll);
+    bool p_in_smem = true;
+    const size_t smem = finalize_smem(em, &p_in_smem);
+    f.p_in_smem = p_in_smem ? 1 : 0;
+    em_finalize_kernel<<<em->path ? em->KP : em->k, 128, smem, em->ctx->gpus[g].stream>>>(f);
     MLB_CUDA(cudaGetLastError());
     ++em->launches;
+    return MLB_OK;
+}
+
+// ---------------------------------------------------------------- direct path: buffers and launches
+
+using EmDirectKernelFn = void (*)(EmDirectArgs);
+static EmDirectKernelFn direct_e_kernel_for(int NB)
+{
+    return NB == 1 ? em_direct_e_kernel<1> : NB == 2 ? em_direct_e_kernel<2> : em_direct_e_kernel<0>;
+}
+
+// Super-chunks: every virtual shard's chunks are cut into at most kDrSuperPerVshard contiguous runs (a function of N only).
+static void direct_layout(mlb_em* em, int vshard, std::vector<int64_t>& point_bounds)
+{
+    const Layout& lay = em->data->lay;
+    const int64_t lo = lay.vshard_chunk[vshard], hi = lay.vshard_chunk[vshard + 1];
+    const int64_t n = std::min<int64_t>(hi - lo, kDrSuperPerVshard);
+    for (int64_t j = 0; j <= n; ++j) {
+        if (n == 0) break;
+        const int64_t chunk_idx = lo + (hi - lo) * j / n;
+        point_bounds.push_back(std::min<int64_t>(chunk_idx * lay.chunk, lay.n_total));
+    }
+}
+
+static int direct_prepare(mlb_em* em)
+{
+    EmDirect& dr = em->dr;
+    if (dr.ready) return MLB_OK;
+    mlb_ctx* ctx = em->ctx;
+    const int vpg = ctx->vshards_per_gpu();
+    std::vector<int2> tiles;
+    for (int mt = 0; mt <= dr.NB; ++mt)
+        for (int nt = mt; nt <= dr.NB; ++nt) tiles.push_back(make_int2(mt, nt));
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        EmDirectGpu& dg = dr.gpus[g];
+        const DataShard& sh = em->data->shards[g];
+        std::vector<long long> begins;
+        for (int j = 0; j < vpg; ++j) {
+            std::vector<int64_t> pb;
+            direct_layout(em, gpu.rank * vpg + j, pb);
+            // consecutive shards share a boundary: keep the first entry only for the first non-empty shard
+            for (size_t i = begins.empty() ? 0 : 1; i < pb.size(); ++i) begins.push_back(static_cast<long long>(pb[i] - sh.begin));
+        }
+        if (begins.empty()) begins.push_back(0);
+        dg.n_sc = static_cast<int>(begins.size()) - 1;
+        const int64_t n = std::max<int64_t>(1, sh.n());
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.r, sizeof(double) * n * dr.KPr, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.ll_tile, sizeof(double) * ((n + kDrTile - 1) / kDrTile), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.partials, sizeof(double) * std::max(1, dg.n_sc) * static_cast<size_t>(dr.SVd), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.vsum, sizeof(double) * kVirtualShards * static_cast<size_t>(dr.SVd), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(dg.vsum, 0, sizeof(double) * kVirtualShards * static_cast<size_t>(dr.SVd), gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.sc_begin, sizeof(long long) * begins.size(), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(dg.sc_begin, begins.data(), sizeof(long long) * begins.size(), cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.tile_tab, sizeof(int2) * tiles.size(), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMemcpyAsync(dg.tile_tab, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, gpu.stream));
+        const auto e_kernel = direct_e_kernel_for(dr.NB);
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(e_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dr.smem_e)));
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em_direct_m_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(dr.smem_m)));
+        int per_e = 0, per_m = 0, sms = 0;
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_e, reinterpret_cast<const void*>(e_kernel), kDrThreads, dr.smem_e));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_m, reinterpret_cast<const void*>(em_direct_m_kernel), kDrThreads, dr.smem_m));
+        MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
+        MLB_REQUIRE(per_e >= 1 && per_m >= 1, "EM direct kernels do not fit on an SM (D=%d, K=%d)", em->d, em->k);
+        dg.grid_e = per_e * sms;
+        dg.grid_m = per_m * sms;
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));   // `begins` and `tiles` are locals
+        return MLB_OK;
+    }));
+    dr.ready = true;
+    return MLB_OK;
+}
+
+static EmDirectArgs direct_args(const mlb_em* em, int g)
+{
+    const EmDirect& dr = em->dr;
+    const EmDirectGpu& dg = dr.gpus[g];
+    const DataShard& sh = em->data->shards[g];
+    EmDirectArgs a{};
+    a.x = sh.x; a.n_local = sh.n();
+    a.d = em->d; a.k = em->k; a.DP = dr.DP; a.KPr = dr.KPr;
+    a.shift = sh.shift;
+    a.img = dg.img;
+    a.r = dg.r; a.ll_tile = dg.ll_tile;
+    a.counter = em->gpus[g].counter;
+    a.cb = dr.cb;
+    a.sc_begin = dg.sc_begin; a.n_sc = dg.n_sc;
+    a.partials = dg.partials; a.svd = dr.SVd;
+    a.cg = dr.cg; a.tiles_per_range = dr.tiles_per_range; a.n_ranges = dr.n_ranges;
+    a.tile_tab = dg.tile_tab;
+    return a;
+}
+
+static int launch_direct_e(mlb_em* em, int g, const EmDirectArgs& a)
+{
+    Gpu& gpu = em->ctx->gpus[g];
+    const long long ntiles = (a.n_local + kDrTile - 1) / kDrTile;
+    if (ntiles == 0) return MLB_OK;
+    MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
+    direct_e_kernel_for(em->dr.NB)<<<static_cast<unsigned>(std::min<long long>(em->dr.gpus[g].grid_e, ntiles)), kDrThreads, em->dr.smem_e, gpu.stream>>>(a);
+    MLB_CUDA(cudaGetLastError());
+    ++em->launches;
+    return MLB_OK;
+}
+
+// The M kernel over the super-chunks (the E tiles' log-likelihood sums folded in when with_ll), then nothing else: the
+// caller reduces, exchanges and refreshes.
+static int launch_direct_m(mlb_em* em, int g, const EmDirectArgs& a, bool with_ll)
+{
+    Gpu& gpu = em->ctx->gpus[g];
+    if (a.n_sc == 0) return MLB_OK;
+    if (with_ll) {
+        em_direct_ll_kernel<<<a.n_sc, 32, 0, gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        ++em->launches;
+    } else {
+        // no E-step behind these statistics: the log-likelihood slots must still be defined
+        for (int sc = 0; sc < a.n_sc; ++sc)
+            MLB_CUDA(cudaMemsetAsync(a.partials + static_cast<size_t>(sc) * a.svd + static_cast<size_t>(em->k) * em->dr.L, 0, sizeof(double) * 8, gpu.stream));
+    }
+    const int ngroups = (a.k + a.cg - 1) / a.cg;
+    const long long nitems = static_cast<long long>(a.n_sc) * ngroups * a.n_ranges;
+    MLB_REQUIRE(nitems < (1ll << 31), "EM direct path: too many work items");
+    MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
+    em_direct_m_kernel<<<static_cast<unsigned>(std::min<long long>(em->dr.gpus[g].grid_m, nitems)), kDrThreads, em->dr.smem_m, gpu.stream>>>(a);
+    MLB_CUDA(cudaGetLastError());
+    ++em->launches;
+    return MLB_OK;
+}
+
+static int direct_reduce(mlb_em* em)
+{
+    std::vector<double*> partials, vsum;
+    for (EmDirectGpu& dg : em->dr.gpus) { partials.push_back(dg.partials); vsum.push_back(dg.vsum); }
+    MLB_TRY(reduce_and_exchange_units(em->data, partials, vsum, em->dr.SVd, em->dr.scratch, em->dr.sc_bounds));
+    em->launches += static_cast<int64_t>(em->ctx->gpus.size());
+    return MLB_OK;
+}
+
+// One iteration on the direct kernels: E, M, reduction + exchange, parameter refresh into the other theta slot.
+static int enqueue_step_direct(mlb_em* em)
+{
+    MLB_TRY(direct_prepare(em));
+    mlb_ctx* ctx = em->ctx;
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        const EmDirectArgs a = direct_args(em, g);
+        MLB_TRY(em->gpus[g].timer.begin(gpu.stream));
+        MLB_TRY(launch_direct_e(em, g, a));
+        MLB_TRY(launch_direct_m(em, g, a, true));
+        MLB_TRY(em->gpus[g].timer.end(gpu.stream));
+        return MLB_OK;
+    }));
+    MLB_TRY(direct_reduce(em));
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, 2, em->cur ^ 1, true); }));
+    em->r_direct_valid = true;
+    return MLB_OK;
+}
+
+// Chooses the path of the next step from kappa of the parameters just refreshed.  enqueue: the copy of kappa into the
+// object's pinned buffer, ordered behind the refresh; finish: after the stream has been synchronised.
+static int route_enqueue(mlb_em* em)
+{
+    if (!em->dr.capable) return MLB_OK;
+    Gpu& gpu = em->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    if (!em->kappa_host) MLB_CUDA(cudaMallocHost(&em->kappa_host, sizeof(double) * em->k));
+    MLB_CUDA(cudaMemcpyAsync(em->kappa_host, em->dr.gpus[0].kappa, sizeof(double) * em->k, cudaMemcpyDeviceToHost, gpu.stream));
+    return MLB_OK;
+}
+
+static void route_finish(mlb_em* em)
+{
+    em->kappa_max = 0.0;
+    if (em->dr.capable && em->kappa_host)
+        for (int i = 0; i < em->k; ++i) {
+            const double v = em->kappa_host[i];
+            if (v != v) em->kappa_max = std::numeric_limits<double>::infinity();   // NaN: a component has collapsed
+            else if (v > em->kappa_max) em->kappa_max = v;
+        }
+    const bool direct = em->path == 0 || em->forced_path == 3 || (em->dr.capable && em->kappa_max > kKappaDirect);
+    em->route = direct ? 3 : em->path;
+}
+
+static int update_route(mlb_em* em)
+{
+    MLB_TRY(route_enqueue(em));
+    MLB_CUDA(cudaStreamSynchronize(em->ctx->gpus[0].stream));
+    route_finish(em);
     return MLB_OK;
 }
 
@@ -764,14 +1070,22 @@ static int enqueue_step_plain(mlb_em* em)
     MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV, em->reduce_scratch));
     em->launches += static_cast<int64_t>(ctx->gpus.size());
     MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
-        return launch_finalize(em, g, true, em->cur ^ 1, true);
+        return launch_finalize(em, g, 1, em->cur ^ 1, true);
     }));
+    em->r_direct_valid = false;
     return MLB_OK;
 }
 
 static int enqueue_step(mlb_em* em)
 {
     mlb_ctx* ctx = em->ctx;
+    if (em->route == 3) {
+        MLB_TRY(enqueue_step_direct(em));
+        em->cur ^= 1;
+        em->last_path = 3;
+        return MLB_OK;
+    }
+    em->last_path = em->path;
     // Graph replay: one local GPU, no collective in the step, no per-launch event timing, and the scratch buffers
     // already sized by two ordinary steps (nothing may allocate while a stream is being captured).
     const bool graphable = ctx->gpus.size() == 1 && ctx->world == 1 && !em->gpus[0].timer.enabled && em->plain_steps >= 2;
@@ -803,8 +1117,55 @@ static int enqueue_step(mlb_em* em)
     }
     MLB_CUDA(cudaGraphLaunch(exec, gpu.stream));
     em->launches += em->launches_per_step;
+    em->r_direct_valid = false;
     em->cur ^= 1;
     return MLB_OK;
+}
+
+// Start of a direct M-step that has no parameters behind it: every component's image says "mean = shift" (delta = 0,
+// which is all the M kernel reads) and the means themselves are set to the shift.
+__global__ void em_direct_origin_kernel(double* img, long long img_len, double* means, const double* shift, int d, int k)
+{
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < img_len) img[i] = 0.0;
+    if (i < static_cast<long long>(d) * k) means[i] = shift[i % d];
+}
+
+// maximisation_step on the direct kernels from the responsibilities in the direct R buffer.  from_origin: there are no
+// parameters yet, so a first pass about the shift finds the means and a second pass about those means gives the
+// covariances without cancellation (the reference makes the same two passes, EM.cpp:229 then :246-248); otherwise one
+// pass about the current means.
+static int direct_mstep_from_r(mlb_em* em, bool from_origin)
+{
+    mlb_ctx* ctx = em->ctx;
+    for (int pass = 0; pass < (from_origin ? 2 : 1); ++pass) {
+        MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+            if (pass == 0 && from_origin) {
+                const long long len = static_cast<long long>(em->k) * em->dr.IMG;
+                const long long total = std::max<long long>(len, static_cast<long long>(em->d) * em->k);
+                em_direct_origin_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, gpu.stream>>>(em->dr.gpus[g].img, len, em->means(g), em->data->shards[g].shift, em->d, em->k);
+                MLB_CUDA(cudaGetLastError());
+                ++em->launches;
+            }
+            return launch_direct_m(em, g, direct_args(em, g), false);
+        }));
+        MLB_TRY(direct_reduce(em));
+        MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, 2, em->cur, false); }));
+    }
+    return MLB_OK;
+}
+
+static int direct_import_r(mlb_em* em, std::vector<double*>& dev)
+{
+    return for_each_gpu(em->ctx, [&](int g, Gpu& gpu) -> int {
+        const int64_t n = em->data->shards[g].n();
+        if (n == 0) return MLB_OK;
+        const long long total = static_cast<long long>(n) * em->dr.KPr;
+        em_split_import_r_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, gpu.stream>>>(dev[g], n, n, em->k, em->dr.KPr, em->dr.gpus[g].r);
+        MLB_CUDA(cudaGetLastError());
+        ++em->launches;
+        return MLB_OK;
+    });
 }
 
 // maximisation_step from responsibilities already on the devices: dev[g] is column-major, local rows of GPU g, leading
@@ -812,31 +1173,40 @@ static int enqueue_step(mlb_em* em)
 static int mstep_from_device(mlb_em* em, std::vector<double*>& dev, int rc)
 {
     mlb_ctx* ctx = em->ctx;
-    if (rc == MLB_OK) {
-        rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int {
-            const int64_t n = em->data->shards[g].n();
-            if (em->path == 2) {
-                if (n == 0) return MLB_OK;
-                const long long total = static_cast<long long>(n) * em->KP;
-                em_split_import_r_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->gpus[g].stream>>>(dev[g], n, n, em->k, em->KP, em->gpus[g].r);
-                MLB_CUDA(cudaGetLastError());
-                ++em->launches;
-                return launch_split(em, g, em->gpus[g].theta[em->cur], false, false);
-            }
-            EmArgs a = base_args(em, g);
-            a.r_in = dev[g];
-            a.r_ld = std::max<int64_t>(1, n);  // device copy: local rows only
-            return launch_em(em, em->fn_mstep, a, g, em->gpus[g].grid);
-        });
-        if (rc == MLB_OK) {
+    auto body = [&]() -> int {
+        const bool direct_only = em->path == 0 || em->forced_path == 3;
+        if (!direct_only) {
+            MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int {
+                const int64_t n = em->data->shards[g].n();
+                if (em->path == 2) {
+                    if (n == 0) return MLB_OK;
+                    const long long total = static_cast<long long>(n) * em->KP;
+                    em_split_import_r_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->gpus[g].stream>>>(dev[g], n, n, em->k, em->KP, em->gpus[g].r);
+                    MLB_CUDA(cudaGetLastError());
+                    ++em->launches;
+                    return launch_split(em, g, em->gpus[g].theta[em->cur], false, false);
+                }
+                EmArgs a = base_args(em, g);
+                a.r_in = dev[g];
+                a.r_ld = std::max<int64_t>(1, n);  // device copy: local rows only
+                return launch_em(em, em->fn_mstep, a, g, em->gpus[g].grid);
+            }));
             std::vector<double*> partials, vsum;
             for (EmGpu& eg : em->gpus) { partials.push_back(eg.partials); vsum.push_back(eg.vsum); }
-            rc = reduce_and_exchange(em->data, partials, vsum, em->SV, em->reduce_scratch);
+            MLB_TRY(reduce_and_exchange(em->data, partials, vsum, em->SV, em->reduce_scratch));
             em->launches += static_cast<int64_t>(ctx->gpus.size());
+            MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, 1, em->cur, false); }));
+            MLB_TRY(update_route(em));
+            if (em->route != 3) return MLB_OK;
+            // The components sit too far from the centre of the data for moments about the shift: once more about the
+            // means just found.
         }
-        if (rc == MLB_OK)
-            rc = for_each_gpu(ctx, [&](int g, Gpu&) -> int { return launch_finalize(em, g, true, em->cur, false); });
-    }
+        MLB_TRY(direct_prepare(em));
+        MLB_TRY(direct_import_r(em, dev));
+        MLB_TRY(direct_mstep_from_r(em, direct_only));
+        return update_route(em);
+    };
+    if (rc == MLB_OK) rc = body();
     // on every path: a pinned source of staged_h2d is still being read by the DMA engine until the stream is idle
     const int rc_sync = mlb_ctx_synchronize(ctx);
     if (rc == MLB_OK) rc = rc_sync;
@@ -844,6 +1214,53 @@ static int mstep_from_device(mlb_em* em, std::vector<double*>& dev, int rc)
         if (dev[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(dev[g], ctx->gpus[g].stream); }
     if (rc == MLB_OK) { em->have_params = true; em->have_step = false; }
     return rc;
+}
+
+// calculate_sample_covariance (EM.cpp:265-272) on the direct kernels: the M kernel for ONE component with unit
+// responsibilities about the shift (a private all-zero image: delta = 0), current parameters untouched.
+static int direct_sample_covariance(mlb_em* em, double* cov_out)
+{
+    MLB_TRY(direct_prepare(em));
+    mlb_ctx* ctx = em->ctx;
+    EmDirect& dr = em->dr;
+    const int d = em->d;
+    std::vector<double*> tmp(ctx->gpus.size(), nullptr);
+    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        MLB_CUDA(cudaMallocFromPoolAsync(&tmp[g], sizeof(double) * dr.IMG, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(tmp[g], 0, sizeof(double) * dr.IMG, gpu.stream));
+        EmDirectArgs a = direct_args(em, g);
+        a.img = tmp[g];
+        a.k = 1;
+        a.unit_r = 1;
+        return launch_direct_m(em, g, a, false);
+    });
+    if (rc == MLB_OK) rc = direct_reduce(em);
+    std::vector<double> host(static_cast<size_t>(kVirtualShards) * dr.L);
+    if (rc == MLB_OK) {
+        Gpu& gpu0 = ctx->gpus[0];
+        MLB_CUDA(cudaSetDevice(gpu0.device));
+        MLB_CUDA(cudaMemcpy2DAsync(host.data(), sizeof(double) * dr.L, dr.gpus[0].vsum, sizeof(double) * dr.SVd, sizeof(double) * dr.L, kVirtualShards,
+                                   cudaMemcpyDeviceToHost, gpu0.stream));
+    }
+    const int rc_sync = mlb_ctx_synchronize(ctx);
+    for (size_t g = 0; g < tmp.size(); ++g)
+        if (tmp[g]) { cudaSetDevice(ctx->gpus[g].device); cudaFreeAsync(tmp[g], ctx->gpus[g].stream); }
+    MLB_TRY(rc);
+    MLB_TRY(rc_sync);
+    em->r_direct_valid = false;
+    const int NBa = dr.NB + 1;
+    auto stat = [&](int mt, int nt, int row, int col) { return tree8(host.data() + dr_tile_index(NBa, mt, nt) * 64 + row * 8 + col, dr.L); };
+    const double count = stat(dr.NB, dr.NB, 0, 0);
+    std::vector<double> m1(d);
+    for (int a = 0; a < d; ++a) m1[a] = stat(a / 8, dr.NB, a % 8, 0);
+    for (int a = 0; a < d; ++a)
+        for (int b = a; b < d; ++b) {
+            const double m2 = stat(a / 8, b / 8, a % 8, b % 8);
+            const double cv = (m2 - m1[a] * m1[b] / count) / (count - 1.0);
+            cov_out[a + static_cast<size_t>(b) * d] = cv;
+            cov_out[b + static_cast<size_t>(a) * d] = cv;
+        }
+    return MLB_OK;
 }
 
 // One-hot responsibilities (Clustering.cpp:76,87) from labels: r[i + k * ld] = (labels[i] == k).
@@ -882,16 +1299,17 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
     MLB_REQUIRE(ctx && data && out, "mlb_em_create: null argument");
     MLB_REQUIRE(data->ctx == ctx, "mlb_em_create: data belongs to another context");
     MLB_REQUIRE(k >= 1, "mlb_em_create: number of components must be positive");
+    MLB_REQUIRE(data->d <= kDirectMaxDim, "mlb_em_create: D=%d not supported by this build (D <= %d)", data->d, kDirectMaxDim);
     static const int dps[] = {4, 8, 16}, kps[] = {8, 16, 32};
     const bool fused = data->d <= 16 && k <= 32;
-    int DP, KP, NT;
+    const bool split = !fused && data->d <= 64 && k <= 256;
+    int DP = 0, KP = 0, NT = 0;
     if (fused) {
         DP = pad_to(data->d, dps, 3);
         KP = pad_to(k, kps, 3);
         NT = KP / 8;
-    } else {
+    } else if (split) {
         // split path: D padded to a multiple of 4, components in groups of 16 (K <= 16), 32 (K <= 32) or 64
-        MLB_REQUIRE(data->d <= 64 && k <= 256, "mlb_em_create: D=%d, K=%d not supported by this build (D <= 64, K <= 256)", data->d, k);
         DP = (data->d + 3) / 4 * 4;
         const int KG = k > 32 ? 64 : (k > 16 ? 32 : 16);
         KP = (k + KG - 1) / KG * KG;
@@ -899,14 +1317,19 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
     }
     auto* em = new mlb_em;
     em->ctx = ctx; em->data = data; em->d = data->d; em->k = k;
-    em->path = fused ? 1 : 2;
-    em->DP = DP; em->KP = KP; em->NT = NT; em->NE = em_ne(DP); em->NM = em_nm(DP); em->SV = em_sv(DP, KP);
+    em->path = fused ? 1 : split ? 2 : 0;   // 0: only the direct kernels take this shape (D > 64 or K > 256)
+    em->route = em->path ? em->path : 3;
+    if (const char* env = std::getenv("MLB200_EM_PATH"))   // developer override: "direct" forces the direct kernels
+        if (std::strcmp(env, "direct") == 0) em->forced_path = 3;
+    if (em->path) {
+        em->DP = DP; em->KP = KP; em->NT = NT; em->NE = em_ne(DP); em->NM = em_nm(DP); em->SV = em_sv(DP, KP);
+    }
     if (fused) {
         em->fn_step = em_kernel_for<0>(DP, KP);
         em->fn_mstep = em_kernel_for<1>(DP, KP);
         em->fn_emit = em_kernel_for<2>(DP, KP);
         em->smem_fused = DP <= 8 ? em_small_smem_bytes(DP, KP) : em_smem_bytes(DP, KP);
-    } else {
+    } else if (split) {
         em->fn_split_e = NT == 8 ? em_split_e_kernel<8> : NT == 4 ? em_split_e_kernel<4> : em_split_e_kernel<2>;
         // feature tiles per warp of the M kernel: the choice that wastes the fewest tile slots (ties: the larger)
         int best_waste = 1 << 30;
@@ -920,9 +1343,9 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
         em->smem_split_e = em_split_e_smem(NT, DP, KP);
         em->smem_split_m = em_split_m_smem(NT, DP);
     }
-    // E-step slots, in the order the kernel enumerates them (see em_ne above); (a, b) with a <= b.
-    em->feat_e.assign(static_cast<size_t>(em->NE) * 4, make_int2(-1, -1));
-    {
+    if (em->path) {
+        // E-step slots, in the order the kernel enumerates them (see em_ne above); (a, b) with a <= b.
+        em->feat_e.assign(static_cast<size_t>(em->NE) * 4, make_int2(-1, -1));
         const int DQ = DP / 4, J0 = em_ne_offdiag(DP);
         auto put = [&](int j, int c, int a, int b) { em->feat_e[static_cast<size_t>(j) * 4 + c] = make_int2(std::min(a, b), std::max(a, b)); };
         for (int a = 0; a < DP - 4; ++a)
@@ -940,10 +1363,8 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
             }
         for (int m = 0; m < DQ; ++m)
             for (int c = 0; c < 4; ++c) em->feat_e[static_cast<size_t>(em->NE - DQ + m) * 4 + c] = make_int2(4 * m + c, DP);
-    }
-    // M-step features as offsets into a Z row: [0,DP) coordinates, DP the constant 1, DP+1 a zero.
-    em->feat_m.assign(static_cast<size_t>(em->NM) * 8, make_int2(DP + 1, DP + 1));
-    {
+        // M-step features as offsets into a Z row: [0,DP) coordinates, DP the constant 1, DP+1 a zero.
+        em->feat_m.assign(static_cast<size_t>(em->NM) * 8, make_int2(DP + 1, DP + 1));
         size_t f = 0;
         em->feat_m[f++] = make_int2(DP, DP);
         for (int a = 0; a < DP; ++a) em->feat_m[f++] = make_int2(a, DP);
@@ -959,32 +1380,69 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
             em->feat_m[f] = ab;
         }
     }
+    {
+        // direct kernels: shape constants (the large buffers are allocated when the path is first taken)
+        EmDirect& dr = em->dr;
+        dr.capable = true;
+        dr.DP = (em->d + 7) / 8 * 8;
+        dr.NB = dr.DP / 8;
+        dr.KPr = (k + 7) / 8 * 8;
+        dr.IMG = dr_img_len(dr.DP);
+        dr.L = dr_stat_len(dr.DP);
+        const long long svd = static_cast<long long>(k) * dr.L + 8;
+        if (svd >= (1ll << 31)) { delete em; set_error("mlb_em_create: D=%d, K=%d: statistics vector too long", data->d, k); return MLB_EINVAL; }
+        dr.SVd = static_cast<int>(svd);
+        dr.cb = static_cast<int>(std::max<size_t>(1, std::min<size_t>(std::min(16, k), (12 * 1024) / (sizeof(double) * dr.IMG))));
+        const int T = dr_tiles(dr.NB);
+        if (T <= 4 * kDrSlots) {
+            const int by_smem = static_cast<int>((96 * 1024) / (sizeof(double) * 2 * kDrSub * (dr.DP + 12))) - 1;
+            dr.cg = std::max(1, std::min({16, k, 4 * kDrSlots / T, by_smem}));
+            dr.tiles_per_range = T;
+            dr.n_ranges = 1;
+        } else {
+            dr.cg = 1;
+            dr.tiles_per_range = 4 * kDrSlots;
+            dr.n_ranges = (T + 4 * kDrSlots - 1) / (4 * kDrSlots);
+        }
+        dr.smem_e = em_direct_e_smem(dr.DP, dr.cb);
+        dr.smem_m = em_direct_m_smem(dr.DP, dr.cg, em->d);
+        dr.sc_bounds[0] = 0;
+        for (int v = 0; v < kVirtualShards; ++v)
+            dr.sc_bounds[v + 1] = dr.sc_bounds[v] + std::min<int64_t>(data->lay.vshard_chunk[v + 1] - data->lay.vshard_chunk[v], kDrSuperPerVshard);
+        dr.gpus.resize(ctx->gpus.size());
+    }
     em->gpus.resize(ctx->gpus.size());
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         EmGpu& eg = em->gpus[g];
+        EmDirectGpu& dg = em->dr.gpus[g];
         const DataShard& sh = data->shards[g];
-        const size_t theta_len = static_cast<size_t>(em_theta_len(DP, KP));
-        MLB_CUDA(cudaMallocFromPoolAsync(&eg.theta[0], sizeof(double) * theta_len, gpu.pool, gpu.stream));
-        MLB_CUDA(cudaMallocFromPoolAsync(&eg.theta[1], sizeof(double) * theta_len, gpu.pool, gpu.stream));
         MLB_CUDA(cudaMallocFromPoolAsync(&eg.params, sizeof(double) * em->params_len(), gpu.pool, gpu.stream));
-        MLB_CUDA(cudaMallocFromPoolAsync(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.pool, gpu.stream));
-        MLB_CUDA(cudaMallocFromPoolAsync(&eg.vsum, sizeof(double) * kVirtualShards * em->SV, gpu.pool, gpu.stream));
         MLB_CUDA(cudaMallocFromPoolAsync(&eg.ll, sizeof(double) * kLlRing, gpu.pool, gpu.stream));
         MLB_CUDA(cudaMallocFromPoolAsync(&eg.ll_counter, sizeof(unsigned long long), gpu.pool, gpu.stream));
         MLB_CUDA(cudaMemsetAsync(eg.ll_counter, 0, sizeof(unsigned long long), gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&eg.counter, sizeof(unsigned), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.img, sizeof(double) * static_cast<size_t>(k) * em->dr.IMG, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&dg.kappa, sizeof(double) * k, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(dg.kappa, 0, sizeof(double) * k, gpu.stream));
         {
-            const size_t fin_smem = sizeof(double) * (3 * em->d * em->d + 3 * em->d);
+            const size_t fin_smem = finalize_smem(em, nullptr);
             if (fin_smem > 48 * 1024)
                 MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(em_finalize_kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fin_smem)));
         }
-        MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_m, sizeof(int2) * em->feat_m.size(), gpu.pool, gpu.stream));
-        MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_e, sizeof(int2) * em->feat_e.size(), gpu.pool, gpu.stream));
-        MLB_CUDA(cudaMallocFromPoolAsync(&eg.counter, sizeof(unsigned), gpu.pool, gpu.stream));
-        MLB_CUDA(cudaMemsetAsync(eg.vsum, 0, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
-        MLB_CUDA(cudaMemcpyAsync(eg.feat_m, em->feat_m.data(), sizeof(int2) * em->feat_m.size(), cudaMemcpyHostToDevice, gpu.stream));
-        MLB_CUDA(cudaMemcpyAsync(eg.feat_e, em->feat_e.data(), sizeof(int2) * em->feat_e.size(), cudaMemcpyHostToDevice, gpu.stream));
         int sms = 0;
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
+        if (em->path) {
+            const size_t theta_len = static_cast<size_t>(em_theta_len(DP, KP));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.theta[0], sizeof(double) * theta_len, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.theta[1], sizeof(double) * theta_len, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * em->SV, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.vsum, sizeof(double) * kVirtualShards * em->SV, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_m, sizeof(int2) * em->feat_m.size(), gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_e, sizeof(int2) * em->feat_e.size(), gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMemsetAsync(eg.vsum, 0, sizeof(double) * kVirtualShards * em->SV, gpu.stream));
+            MLB_CUDA(cudaMemcpyAsync(eg.feat_m, em->feat_m.data(), sizeof(int2) * em->feat_m.size(), cudaMemcpyHostToDevice, gpu.stream));
+            MLB_CUDA(cudaMemcpyAsync(eg.feat_e, em->feat_e.data(), sizeof(int2) * em->feat_e.size(), cudaMemcpyHostToDevice, gpu.stream));
+        }
         if (em->path == 1) {
             const size_t smem = em->smem_fused;
             for (EmKernelFn fn : {em->fn_step, em->fn_mstep, em->fn_emit})
@@ -993,7 +1451,7 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
             MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(em->fn_step), kEmThreads, smem));
             MLB_REQUIRE(per_sm >= 1, "mlb_em_create: EM kernel does not fit on an SM");
             eg.grid = per_sm * sms;
-        } else {
+        } else if (em->path == 2) {
             std::vector<int2> off(em->feat_e.size());
             for (size_t i = 0; i < off.size(); ++i) off[i] = em->feat_e[i].x < 0 ? make_int2(DP + 1, DP + 1) : em->feat_e[i];
             MLB_CUDA(cudaMallocFromPoolAsync(&eg.feat_e_off, sizeof(int2) * off.size(), gpu.pool, gpu.stream));
@@ -1040,8 +1498,16 @@ int mlb_em_destroy(mlb_em* em)
                           static_cast<void*>(eg.stage), static_cast<void*>(eg.stage_labels), static_cast<void*>(eg.r), static_cast<void*>(eg.ll_tile),
                           static_cast<void*>(eg.feat_e_off)})
             if (ptr) cudaFreeAsync(ptr, em->ctx->gpus[g].stream);
+        if (g < em->dr.gpus.size()) {
+            EmDirectGpu& dg = em->dr.gpus[g];
+            for (void* ptr : {static_cast<void*>(dg.img), static_cast<void*>(dg.kappa), static_cast<void*>(dg.r), static_cast<void*>(dg.ll_tile),
+                              static_cast<void*>(dg.partials), static_cast<void*>(dg.vsum), static_cast<void*>(dg.sc_begin), static_cast<void*>(dg.tile_tab)})
+                if (ptr) cudaFreeAsync(ptr, em->ctx->gpus[g].stream);
+        }
     }
     em->reduce_scratch.release(em->ctx);
+    em->dr.scratch.release(em->ctx);
+    if (em->kappa_host) cudaFreeHost(em->kappa_host);
     delete em;
     return MLB_OK;
 }
@@ -1055,10 +1521,11 @@ int mlb_em_set_params(mlb_em* em, const double* means, const double* covariances
         MLB_CUDA(cudaMemcpyAsync(em->means(g), means, sizeof(double) * dk, cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(em->covs(g), covariances, sizeof(double) * kdd, cudaMemcpyHostToDevice, gpu.stream));
         MLB_CUDA(cudaMemcpyAsync(em->weights(g), weights, sizeof(double) * em->k, cudaMemcpyHostToDevice, gpu.stream));
-        MLB_TRY(launch_finalize(em, g, false, em->cur, false));
+        MLB_TRY(launch_finalize(em, g, 0, em->cur, false));
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));  // the host buffers may go away
         return MLB_OK;
     }));
+    MLB_TRY(update_route(em));
     em->have_params = true;
     em->have_step = false;
     return MLB_OK;
@@ -1071,18 +1538,27 @@ int mlb_em_run_steps(mlb_em* em, int steps, double* log_likelihoods)
     MLB_REQUIRE(steps <= kLlRing, "mlb_em_run_steps: at most %d steps per call", kLlRing);
     if (!em->have_params) { set_error("mlb_em_run_steps: parameters not set"); return MLB_ESTATE; }
     const int64_t first = em->steps_done;
+    Gpu& gpu0 = em->ctx->gpus[0];
     for (int s = 0; s < steps; ++s) {
         MLB_TRY(enqueue_step(em));
         ++em->steps_done;
+        // The path of the next step depends on the parameters this one produced: kappa comes back with every step (one
+        // small copy; the last step's rides on the synchronisation the call ends with anyway).
+        MLB_TRY(route_enqueue(em));
+        if (s + 1 < steps) {
+            MLB_CUDA(cudaStreamSynchronize(gpu0.stream));
+            route_finish(em);
+        }
     }
-    if (steps > 0) { em->have_step = true; em->last_path = em->path; }
+    if (steps > 0) em->have_step = true;
     if (log_likelihoods) {
-        Gpu& gpu = em->ctx->gpus[0];
-        MLB_CUDA(cudaSetDevice(gpu.device));
+        MLB_CUDA(cudaSetDevice(gpu0.device));
         for (int s = 0; s < steps; ++s)
-            MLB_CUDA(cudaMemcpyAsync(log_likelihoods + s, em->gpus[0].ll + (first + s) % kLlRing, sizeof(double), cudaMemcpyDeviceToHost, gpu.stream));
+            MLB_CUDA(cudaMemcpyAsync(log_likelihoods + s, em->gpus[0].ll + (first + s) % kLlRing, sizeof(double), cudaMemcpyDeviceToHost, gpu0.stream));
     }
-    return mlb_ctx_synchronize(em->ctx);
+    MLB_TRY(mlb_ctx_synchronize(em->ctx));
+    if (steps > 0) route_finish(em);
+    return MLB_OK;
 }
 
 int mlb_em_step(mlb_em* em, double* log_likelihood)
@@ -1090,6 +1566,26 @@ int mlb_em_step(mlb_em* em, double* log_likelihood)
     MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && log_likelihood, "mlb_em_step: null argument");
     return mlb_em_run_steps(em, 1, log_likelihood);
+}
+
+int mlb_em_force_path(mlb_em* em, int path)
+{
+    MLB_ENTER(em ? em->ctx : nullptr);
+    MLB_REQUIRE(em, "mlb_em_force_path: null argument");
+    MLB_REQUIRE(path == 0 || path == 3, "mlb_em_force_path: path must be 0 (automatic) or 3 (direct-difference kernels)");
+    em->forced_path = path;
+    if (em->have_params) MLB_TRY(update_route(em));
+    else em->route = (path == 3 || em->path == 0) ? 3 : em->path;
+    return MLB_OK;
+}
+
+int mlb_em_conditioning(mlb_em* em, double* kappa_max, int* next_path)
+{
+    MLB_ENTER(em ? em->ctx : nullptr);
+    MLB_REQUIRE(em, "mlb_em_conditioning: null argument");
+    if (kappa_max) *kappa_max = em->kappa_max;
+    if (next_path) *next_path = em->route;
+    return MLB_OK;
 }
 
 int mlb_em_get_params(mlb_em* em, double* means, double* covariances, double* weights)
@@ -1124,6 +1620,7 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
 {
     MLB_ENTER(em ? em->ctx : nullptr);
     MLB_REQUIRE(em && cov_out, "mlb_em_sample_covariance: null argument");
+    if (em->path == 0 || em->forced_path == 3) return direct_sample_covariance(em, cov_out);
     // A one-component M-step with unit responsibilities: theta = 0 for component 0, -inf constants elsewhere.
     // Uses the spare theta slot and leaves the current parameters untouched.  On the fused path the pass runs the
     // 8-component instantiation of the step kernel (a quarter of the tensor-pipe work of a K = 32 step); the chunk
@@ -1237,6 +1734,7 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
     MLB_REQUIRE(em, "mlb_em_emit_range: null argument");
     MLB_REQUIRE(begin >= 0 && count >= 0 && begin + count <= em->data->lay.n_total, "mlb_em_emit_range: range out of bounds");
     if (!em->have_step) { set_error("mlb_em_emit: no step has been run"); return MLB_ESTATE; }
+    if (em->last_path == 3 && !em->r_direct_valid) { set_error("mlb_em_emit: the responsibilities of the last step have been overwritten"); return MLB_ESTATE; }
     if ((!resp_out && !labels_out) || count == 0) return MLB_OK;
     MLB_REQUIRE(!resp_out || ld >= count, "mlb_em_emit_range: leading dimension smaller than the row count");
     mlb_ctx* ctx = em->ctx;
@@ -1260,7 +1758,19 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
             any = true;
             EmGpu& eg = em->gpus[g];
             const int64_t row = lo - begin;
-            if (em->path == 2) {
+            if (em->last_path == 3) {
+                // direct kernels: the responsibilities of the last E-step are resident in the direct R buffer
+                EmSplitArgs a{};
+                a.k = em->k; a.KP = em->dr.KPr; a.r = em->dr.gpus[g].r;
+                a.range_begin = lo - sh.begin;
+                a.range_count = n;
+                a.r_out = resp_out ? eg.stage : nullptr;
+                a.r_out_ld = kStagePoints;
+                a.labels_out = labels_out ? eg.stage_labels : nullptr;
+                em_split_emit_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, gpu.stream>>>(a);
+                MLB_CUDA(cudaGetLastError());
+                ++em->launches;
+            } else if (em->path == 2) {
                 // the responsibilities of the last E-step are resident: transpose them out, argmax for the labels
                 EmSplitArgs a = split_args(em, g, nullptr);
                 a.range_begin = lo - sh.begin;
@@ -1284,8 +1794,7 @@ int mlb_em_emit_range(mlb_em* em, int64_t begin, int64_t count, double* resp_out
             MLB_TRY(launch_em(em, em->fn_emit, a, g, 8 * kSmCount));
             }
             if (resp_out)
-                for (int kk = 0; kk < em->k; ++kk)
-                    MLB_TRY(staged_d2h(gpu, resp_out + row + static_cast<int64_t>(kk) * ld, eg.stage + static_cast<int64_t>(kk) * kStagePoints, sizeof(double) * n));
+                MLB_TRY(staged_d2h_2d(gpu, resp_out + row, sizeof(double) * ld, eg.stage, sizeof(double) * kStagePoints, static_cast<size_t>(em->k), sizeof(double) * n));
             if (labels_out) MLB_TRY(staged_d2h(gpu, labels_out + row, eg.stage_labels, sizeof(unsigned) * n));
             return MLB_OK;
         }));
@@ -1322,8 +1831,13 @@ int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double*
     double *xd = nullptr, *r_tmp = nullptr, *ll_tmp = nullptr;
     MLB_CUDA(cudaMallocFromPoolAsync(&xd, sizeof(double) * cap * d, gpu.pool, gpu.stream));
     int rc = MLB_OK;
+    const bool direct = em->route == 3;
     auto body = [&]() -> int {
-        if (em->path == 2) {
+        if (direct) {
+            MLB_TRY(direct_prepare(em));
+            MLB_CUDA(cudaMallocFromPoolAsync(&r_tmp, sizeof(double) * cap * em->dr.KPr, gpu.pool, gpu.stream));
+            MLB_CUDA(cudaMallocFromPoolAsync(&ll_tmp, sizeof(double) * ((cap + kDrTile - 1) / kDrTile), gpu.pool, gpu.stream));
+        } else if (em->path == 2) {
             MLB_CUDA(cudaMallocFromPoolAsync(&r_tmp, sizeof(double) * cap * em->KP, gpu.pool, gpu.stream));
             MLB_CUDA(cudaMallocFromPoolAsync(&ll_tmp, sizeof(double) * ((cap + 127) / 128) * 2, gpu.pool, gpu.stream));
         }
@@ -1331,7 +1845,25 @@ int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double*
             const int64_t n = std::min<int64_t>(kStagePoints, m - off);
             const double* src = x + off * ld_x;
             MLB_TRY(staged_h2d(gpu, xd, src, static_cast<size_t>(n), sizeof(double) * d, sizeof(double) * ld_x));
-            if (em->path == 2) {
+            if (direct) {
+                // direct E kernel on the staged points with the current images, then the transposing emit kernel
+                EmDirectArgs a = direct_args(em, 0);
+                a.x = xd;
+                a.n_local = n;
+                a.r = r_tmp;
+                a.ll_tile = ll_tmp;
+                MLB_TRY(launch_direct_e(em, 0, a));
+                EmSplitArgs e{};
+                e.k = em->k; e.KP = em->dr.KPr; e.r = r_tmp;
+                e.range_begin = 0;
+                e.range_count = n;
+                e.r_out = resp_out ? eg.stage : nullptr;
+                e.r_out_ld = kStagePoints;
+                e.labels_out = labels_out ? eg.stage_labels : nullptr;
+                em_split_emit_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, gpu.stream>>>(e);
+                MLB_CUDA(cudaGetLastError());
+                ++em->launches;
+            } else if (em->path == 2) {
                 // E kernel on the staged points (responsibilities into r_tmp), then the transposing emit kernel
                 EmSplitArgs a = split_args(em, 0, eg.theta[em->cur]);
                 a.x = xd;
@@ -1367,8 +1899,7 @@ int mlb_em_predict(mlb_em* em, const double* x, int64_t m, int64_t ld_x, double*
                 MLB_TRY(launch_em(em, em->fn_emit, a, 0, 8 * kSmCount));
             }
             if (resp_out)
-                for (int kk = 0; kk < em->k; ++kk)
-                    MLB_TRY(staged_d2h(gpu, resp_out + off + static_cast<int64_t>(kk) * ld_out, eg.stage + static_cast<int64_t>(kk) * kStagePoints, sizeof(double) * n));
+                MLB_TRY(staged_d2h_2d(gpu, resp_out + off, sizeof(double) * ld_out, eg.stage, sizeof(double) * kStagePoints, static_cast<size_t>(em->k), sizeof(double) * n));
             if (labels_out) MLB_TRY(staged_d2h(gpu, labels_out + off, eg.stage_labels, sizeof(unsigned) * n));
             MLB_CUDA(cudaStreamSynchronize(gpu.stream));
         }

@@ -189,6 +189,10 @@ struct ReduceScratch {
 //   vsum[g]:     device, [8][s]; on return every GPU holds all 8 shard vectors.
 // Fixed summation order => deterministic and independent of the GPU count.
 int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s, ReduceScratch& scratch);
+// The same for partial vectors per "unit" other than the chunk (the direct EM kernels' super-chunks): bounds[0..8] are the
+// global unit boundaries of the 8 virtual shards (a function of N only), partials[g] holds the units of GPU g's shards.
+int reduce_and_exchange_units(mlb_data* data, const std::vector<double*>& partials, const std::vector<double*>& vsum, int s, ReduceScratch& scratch,
+                              const int64_t* bounds);
 
 // Copies between host memory that is probably pageable (a numpy array, a std::vector, an Eigen matrix) and the device.
 // A direct cudaMemcpy of pageable memory runs at ~10 GB/s host -> device and ~4 GB/s device -> host on these boxes (one
@@ -204,6 +208,9 @@ int reduce_and_exchange(mlb_data* data, const std::vector<double*>& partials, co
 int staged_h2d(Gpu& gpu, void* dst_device, const void* src, size_t rows, size_t row_bytes, size_t src_stride);
 // staged_d2h: synchronous; on return dst holds the data.
 int staged_d2h(Gpu& gpu, void* dst, const void* src_device, size_t bytes);
+// The same for `rows` rows of `row_bytes` bytes, `src_stride` apart on the device and `dst_stride` apart on the host
+// (one column block of a column-major matrix per row): all rows share the copy threads.
+int staged_d2h_2d(Gpu& gpu, void* dst, size_t dst_stride, const void* src_device, size_t src_stride, size_t rows, size_t row_bytes);
 
 // Event pairs around the launches of one kernel on one stream (roofline timing for bench.py).
 struct KernelTimer {

@@ -53,9 +53,10 @@ __device__ __forceinline__ void km_dmma(double (&acc)[2], double a, double b)
 
 __host__ __device__ inline int km_sv(int d, int KP) { return KP * (d + 1) + 8; }
 
-inline size_t km_smem_bytes(int DP, int KP)
+// nw = warps per CTA of the assignment kernel (16 points each)
+inline size_t km_smem_bytes(int DP, int KP, int nw = 4)
 {
-    return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + 2 * kKmTile * (DP + 4) + DP + 16) + sizeof(int) * 3 * kKmTile;
+    return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + 2 * static_cast<size_t>(nw) * 16 * (DP + 4) + DP + 32) + sizeof(int) * 3 * nw * 16;
 }
 inline size_t km_stats_smem_bytes(int d, int KP)
 {
@@ -110,19 +111,23 @@ constexpr int kKmSub = 16;   // points per warp sub-tile
 // COMPACT: the chunk's 8 scalars go to partials[chunk * 8] (centroid blocks, prediction) instead of to their slots in the
 // chunk's full statistics vector.  A template parameter, not run-time addressing: with the addressing made generic ptxas
 // allocates the main loop differently (125 instead of 149 registers at D = 32) and the kernel is 5 % slower on C5.
-template <int DP, bool COMPACT>
-__global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
+// NW = warps per CTA.  The centroid image is shared by the whole CTA, so when it is what limits the CTAs per SM (64 KB at
+// D = 32, K = 256: two CTAs of four warps, 8 warps per SM) one wide CTA keeps twice the warps resident on the same image
+// (NW = 16: 4 per sub-partition), which is what hides the fixed issue latency between a warp's DMMAs and the global loads
+// of the refinement (ncu r01j: 36 % of the stall samples were `wait`, 14.5 % long scoreboard, the FP64 pipe 69 % busy).
+template <int DP, bool COMPACT, int NW>
+__global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
 {
-    constexpr int DQ = DP / 4, XS = DP + 4;
+    constexpr int DQ = DP / 4, XS = DP + 4, kKmTile = NW * 16, kKmThreads = NW * 32;
     extern __shared__ __align__(16) double sm[];
     const int KP = p.KP, d = p.d, SD = d + 1;
     double* Bf = sm;                                  // DP * KP
     double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
     double* Xb = nrm + KP;                            // [4 warps][2 buffers][16][XS], raw coordinates (padding columns zero)
     double* sh = Xb + 2 * kKmTile * XS;               // DP
-    double* red = sh + DP;                            // 16
-    int* labs_all = reinterpret_cast<int*>(red + 16); // [4][16]: the filter's verdict (~label: ambiguous under its rounding bound)
-    unsigned* oldl_all = reinterpret_cast<unsigned*>(labs_all + kKmTile);  // [4][2][16]: previous labels
+    double* red = sh + DP;                            // 32
+    int* labs_all = reinterpret_cast<int*>(red + 32); // [NW][16]: the filter's verdict (~label: ambiguous under its rounding bound)
+    unsigned* oldl_all = reinterpret_cast<unsigned*>(labs_all + kKmTile);  // [NW][2][16]: previous labels
     __shared__ int s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
@@ -177,16 +182,16 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
         double inertia_acc = 0.0;
         int changed_acc = 0;
 
-        // warp w takes the sub-tiles w, w + 4, w + 8, ... of the chunk
+        // warp w takes the sub-tiles w, w + NW, w + 2 NW, ... of the chunk
         auto sub_begin = [&](int t) { return p_begin + static_cast<long long>(t) * kKmSub; };
         auto sub_valid = [&](int t) { const long long left = p_end - sub_begin(t); return static_cast<int>(left < kKmSub ? left : kKmSub); };
         if (warp < nsubs) stage(sub_begin(warp), sub_valid(warp), 0);
         int it = 0;
-        for (int t = warp; t < nsubs; t += 4, ++it) {
+        for (int t = warp; t < nsubs; t += NW, ++it) {
             const long long tile0 = sub_begin(t);
             const int nvalid = sub_valid(t);
-            if (t + 4 < nsubs) {
-                stage(sub_begin(t + 4), sub_valid(t + 4), (it + 1) & 1);
+            if (t + NW < nsubs) {
+                stage(sub_begin(t + NW), sub_valid(t + NW), (it + 1) & 1);
                 km_cp_async_wait<1>();
             } else {
                 km_cp_async_wait<0>();
@@ -332,11 +337,111 @@ __global__ void __launch_bounds__(kKmThreads) km_assign_kernel(const KmArgs p)
             inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, off);
             changed_acc += __shfl_xor_sync(0xffffffffu, changed_acc, off);
         }
-        if (lane == 0) { red[warp] = inertia_acc; red[8 + warp] = static_cast<double>(changed_acc); }
+        if (lane == 0) { red[warp] = inertia_acc; red[16 + warp] = static_cast<double>(changed_acc); }
         __syncthreads();
         if (tid == 0) {
-            out[KP * SD] = (red[0] + red[1]) + (red[2] + red[3]);
-            out[KP * SD + 1] = (red[8] + red[9]) + (red[10] + red[11]);
+            // fixed pairwise tree over the NW warps
+            double a[NW], b[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { a[w] = red[w]; b[w] = red[16 + w]; }
+#pragma unroll
+            for (int span = 1; span < NW; span <<= 1)
+#pragma unroll
+                for (int w = 0; w + span < NW; w += 2 * span) { a[w] += a[w + span]; b[w] += b[w + span]; }
+            out[KP * SD] = a[0];
+            out[KP * SD + 1] = b[0];
+        }
+        if (tid >= 2 && tid < 8) out[KP * SD + tid] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------- assignment for D > 64: the reference's scan
+// The filter above keeps a point's coordinates in registers (DQ = D / 4 per lane and sub-tile), which stops paying beyond
+// D = 64.  Wider points take KMeans.cpp:153-165 as written: every point against every centroid, (x - c).squaredNorm() as
+// the sequential fused multiply-add chain, strict <, lowest index wins.  One thread per point; the point tile and a block
+// of 32 centroids sit in shared memory (rows of the tile padded to an odd stride, centroid reads are broadcasts).  Same
+// outputs as km_assign_kernel: labels, per chunk the inertia and the number of changed labels, optionally the distances.
+constexpr int kKmExactTile = 128;
+constexpr int kKmExactBlock = 32;
+
+inline size_t km_exact_smem_bytes(int d)
+{
+    return sizeof(double) * (static_cast<size_t>(kKmExactTile) * (d | 1) + static_cast<size_t>(kKmExactBlock) * d + 2 * kKmExactTile);
+}
+
+template <bool COMPACT>
+__global__ void __launch_bounds__(kKmExactTile) km_assign_exact_kernel(const KmArgs p)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int d = p.d, XS = d | 1, KP = p.KP, SD = d + 1;
+    double* X = sm;                                            // [128][XS]
+    double* C = X + static_cast<size_t>(kKmExactTile) * XS;    // [32][d]
+    double* red = C + static_cast<size_t>(kKmExactBlock) * d;  // [2][128]
+    __shared__ int s_next;
+    const int tid = threadIdx.x;
+    const FastDiv by_d(d);
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = static_cast<int>(atomicAdd(p.counter, 1u));
+        __syncthreads();
+        const int chunk = s_next;
+        if (chunk >= p.n_chunks) break;
+        const long long p_begin = static_cast<long long>(chunk) * p.chunk;
+        const long long p_end = p_begin + p.chunk < p.n_local ? p_begin + p.chunk : p.n_local;
+        double inertia_acc = 0.0, changed_acc = 0.0;
+        for (long long tile0 = p_begin; tile0 < p_end; tile0 += kKmExactTile) {
+            const int nvalid = static_cast<int>(p_end - tile0 < kKmExactTile ? p_end - tile0 : kKmExactTile);
+            __syncthreads();   // the previous tile has been consumed
+            const double* xg = p.x + tile0 * d;
+            for (int e = tid; e < nvalid * d; e += kKmExactTile) {
+                const int pt = by_d.div(e);
+                X[pt * XS + (e - pt * d)] = __ldg(xg + e);
+            }
+            const double* row = X + tid * XS;
+            double best = INFINITY;
+            unsigned label = 0;
+            for (int c0 = 0; c0 < p.k; c0 += kKmExactBlock) {
+                const int cb = min(kKmExactBlock, p.k - c0);
+                __syncthreads();   // the previous centroid block has been consumed (first pass: the tile is complete)
+                for (int e = tid; e < cb * d; e += kKmExactTile) C[e] = __ldg(p.craw + static_cast<long long>(c0) * d + e);
+                __syncthreads();
+                if (tid < nvalid) {
+                    for (int kk = 0; kk < cb; ++kk) {
+                        const double* cr = C + kk * d;
+                        double s = 0.0;
+#pragma unroll 4
+                        for (int l = 0; l < d; ++l) {
+                            const double t = row[l] - cr[l];
+                            s = fma(t, t, s);
+                        }
+                        if (s < best) { best = s; label = static_cast<unsigned>(c0 + kk); }
+                    }
+                }
+            }
+            if (tid < nvalid) {
+                inertia_acc += best;
+                if (p.labels[tile0 + tid] != label) changed_acc += 1.0;
+                p.labels[tile0 + tid] = label;
+                if (COMPACT && p.dist_out) p.dist_out[tile0 + tid] = best;
+            }
+        }
+        // the chunk's inertia and changed-label count: a fixed tree over the 128 threads
+        __syncthreads();
+        red[tid] = inertia_acc;
+        red[kKmExactTile + tid] = changed_acc;
+        __syncthreads();
+        for (int s = kKmExactTile / 2; s > 0; s >>= 1) {
+            if (tid < s) {
+                red[tid] += red[tid + s];
+                red[kKmExactTile + tid] += red[kKmExactTile + tid + s];
+            }
+            __syncthreads();
+        }
+        double* out = COMPACT ? p.partials + static_cast<long long>(chunk) * 8 - KP * SD : p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        if (tid == 0) {
+            out[KP * SD] = red[0];
+            out[KP * SD + 1] = red[kKmExactTile];
         }
         if (tid >= 2 && tid < 8) out[KP * SD + tid] = 0.0;
     }
@@ -369,6 +474,7 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
     if (tid < d) sh[tid] = p.shift[tid];
     __syncthreads();
     const double sh0 = lane < d ? sh[lane] : 0.0, sh1 = lane + 32 < d ? sh[lane + 32] : 0.0;
+    const double sh2 = lane + 64 < d ? sh[lane + 64] : 0.0, sh3 = lane + 96 < d ? sh[lane + 96] : 0.0;
     double cnt = 0.0;
 
     for (;;) {
@@ -417,6 +523,8 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
                     double* sk = sums + static_cast<size_t>(kk) * SD;
                     if (lane < d) sk[lane] += xr[lane] - sh0;
                     if (DP > 32 && lane + 32 < d) sk[lane + 32] += xr[lane + 32] - sh1;
+                    if (DP > 64 && lane + 64 < d) sk[lane + 64] += xr[lane + 64] - sh2;
+                    if (DP > 64 && lane + 96 < d) sk[lane + 96] += xr[lane + 96] - sh3;
                     if (reg_counts) cnt += (kk - own_lo == lane) ? 1.0 : 0.0;   // lane j counts cluster own_lo + j
                     else if (lane == 0) sk[d] += 1.0;
                 }
@@ -671,17 +779,39 @@ __global__ void __launch_bounds__(256) km_finish_assign_kernel(const unsigned* _
 
 using KmKernelFn = void (*)(KmArgs);
 
-template <bool COMPACT>
-static KmKernelFn km_kernel_for(int DP)
+template <bool COMPACT, int NW>
+static KmKernelFn km_kernel_for_nw(int DP)
 {
     switch (DP) {
-    case 4: return km_assign_kernel<4, COMPACT>;
-    case 8: return km_assign_kernel<8, COMPACT>;
-    case 16: return km_assign_kernel<16, COMPACT>;
-    case 32: return km_assign_kernel<32, COMPACT>;
-    case 64: return km_assign_kernel<64, COMPACT>;
+    case 4: return km_assign_kernel<4, COMPACT, NW>;
+    case 8: return km_assign_kernel<8, COMPACT, NW>;
+    case 16: return km_assign_kernel<16, COMPACT, NW>;
+    case 32: return km_assign_kernel<32, COMPACT, NW>;
+    case 64: return km_assign_kernel<64, COMPACT, NW>;
     default: return nullptr;
     }
+}
+
+template <bool COMPACT>
+static KmKernelFn km_kernel_for(int DP, int nw)
+{
+    return nw == 16 ? km_kernel_for_nw<COMPACT, 16>(DP) : nw == 8 ? km_kernel_for_nw<COMPACT, 8>(DP) : km_kernel_for_nw<COMPACT, 4>(DP);
+}
+
+// Warps per CTA of the assignment kernel for a centroid block of kb centroids: the choice that keeps the most warps
+// resident per SM (shared memory: one centroid image per CTA; registers: 128 per thread, 16 warps per SM), the narrowest
+// CTA on ties.  A function of the shape only, so every GPU of a job makes the same choice.
+static int km_warps_per_cta(int DP, int kb)
+{
+    constexpr size_t kSmem = 227 * 1024;
+    int best_nw = 4, best_warps = 0;
+    for (int nw : {4, 8, 16}) {
+        const size_t bytes = km_smem_bytes(DP, kb, nw) + 1024;
+        if (bytes > kSmem) continue;
+        const int ctas = static_cast<int>(std::min<size_t>(kSmem / bytes, 16 / nw));
+        if (ctas * nw > best_warps) { best_warps = ctas * nw; best_nw = nw; }
+    }
+    return best_nw;
 }
 
 static KmKernelFn km_stats_small_kernel_for(int DP)
@@ -704,6 +834,7 @@ static KmKernelFn km_stats_kernel_for(int DP)
     case 16: return km_stats_kernel<16, BLOCKED>;
     case 32: return km_stats_kernel<32, BLOCKED>;
     case 64: return km_stats_kernel<64, BLOCKED>;
+    case 128: return km_stats_kernel<128, BLOCKED>;
     default: return nullptr;
     }
 }
@@ -741,6 +872,8 @@ struct mlb_km {
     std::vector<KmGpu> gpus;
     KmKernelFn fn = nullptr, fn_compact = nullptr, fn_stats = nullptr;   // fn_compact: the assignment kernel with compact per-chunk scalars
     bool stats_small = false;
+    bool exact = false;          // D > 64: the reference's scan (km_assign_exact_kernel) instead of the DMMA filter
+    int nw = 4;                  // warps per CTA of the assignment kernel
     size_t smem = 0, smem_stats = 0;
     bool have_centroids = false, have_stats = false;
     int64_t launches = 0;
@@ -751,6 +884,7 @@ namespace mlb {
 
 static int km_prepare(mlb_km* km)
 {
+    if (km->exact) return MLB_OK;   // no filter image: the scan reads the centroids as they are
     return for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
         KmGpu& kg = km->gpus[g];
         for (int b = 0; b < km->nblocks; ++b) {
@@ -781,14 +915,15 @@ static int launch_assign(mlb_km* km, int g, const double* x, long long n, int ch
     a.shift = km->data->shards[g].shift;
     a.chunk = chunk; a.n_chunks = n_chunks;
     a.counter = kg.counter;
-    if (km->nblocks == 1) {
+    if (km->nblocks == 1 || km->exact) {
         a.k = km->k;
+        a.KP = km->KP;   // == KB when the centroids are one block; the exact kernel scans all K whatever the statistics blocks
         a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
         a.labels = labels; a.partials = partials; a.dist_out = dist_out;
         // full statistics vectors (the fit: pstride == SV, scalars at KP * (d + 1)) or 8 scalars per chunk (prediction)
         const KmKernelFn fn = pstride == 8 ? km->fn_compact : km->fn;
         MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-        fn<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+        fn<<<std::min(kg.grid, n_chunks), km->exact ? kKmExactTile : km->nw * 32, km->smem, gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
         ++km->launches;
         return MLB_OK;
@@ -802,7 +937,7 @@ static int launch_assign(mlb_km* km, int g, const double* x, long long n, int ch
         a.cmax = kg.cmax + b;
         a.labels = tmp_lab; a.partials = tmp_scratch; a.dist_out = tmp_dist;
         MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
-        km->fn_compact<<<std::min(kg.grid, n_chunks), kKmThreads, km->smem, gpu.stream>>>(a);
+        km->fn_compact<<<std::min(kg.grid, n_chunks), km->nw * 32, km->smem, gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
         km_combine_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, gpu.stream>>>(tmp_lab, tmp_dist, n, static_cast<unsigned>(b) * km->KB, b == 0, tmp_best_lab, best_dist);
         MLB_CUDA(cudaGetLastError());
@@ -826,21 +961,23 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
     MLB_REQUIRE(k >= 1, "mlb_km_create: number of clusters must be positive");
     const int d = data->d;
     int DP = 0;
-    for (int cand : {4, 8, 16, 32, 64})
+    for (int cand : {4, 8, 16, 32, 64, 128})
         if (d <= cand) { DP = cand; break; }
-    MLB_REQUIRE(DP, "mlb_km_create: D=%d not supported by this build (D <= 64)", d);
+    MLB_REQUIRE(DP, "mlb_km_create: D=%d not supported by this build (D <= 128)", d);
+    const bool exact = DP > 64;   // wide points: the reference's scan instead of the DMMA filter (km_assign_exact_kernel)
     constexpr size_t kSmemLimit = 227 * 1024;
     int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup, KB = KP, nblocks = 1;
     auto stats_bytes = [&](int kp) { return (kp == kKmGroup && DP <= 32) ? km_stats_small_smem_bytes(DP) : km_stats_smem_bytes(d, kp); };
+    auto assign_bytes = [&](int kp) { return exact ? km_exact_smem_bytes(d) : km_smem_bytes(DP, kp); };
     int forced = 0;   // MLB200_KM_BLOCK: developer override (a multiple of 32) that forces small centroid blocks, for tests
     if (const char* env = std::getenv("MLB200_KM_BLOCK")) forced = std::atoi(env) / kKmGroup * kKmGroup;
-    if (std::max(km_smem_bytes(DP, KP), stats_bytes(KP)) > kSmemLimit || (forced >= kKmGroup && forced < KP)) {
+    if (std::max(assign_bytes(KP), stats_bytes(KP)) > kSmemLimit || (forced >= kKmGroup && forced < KP)) {
         // Centroid blocks: the largest block that leaves room for two CTAs per SM if that is at least 128 centroids,
         // else the largest that fits at all.
         auto largest = [&](size_t limit) {
             int kb = 0;
             for (int cand = kKmGroup; cand <= 4096; cand += kKmGroup)
-                if (km_smem_bytes(DP, cand) <= limit && km_stats_smem_bytes(d, cand) <= kSmemLimit) kb = cand;
+                if ((exact || assign_bytes(cand) <= limit) && km_stats_smem_bytes(d, cand) <= kSmemLimit) kb = cand;
             return kb;
         };
         KB = largest(kSmemLimit / 2 - 1024);
@@ -850,12 +987,15 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         nblocks = (k + KB - 1) / KB;
         KP = nblocks * KB;
     }
-    const size_t smem = km_smem_bytes(DP, KB), smem_stats = nblocks == 1 ? stats_bytes(KB) : km_stats_smem_bytes(d, KB);
+    const int nw = exact ? 4 : km_warps_per_cta(DP, KB);
+    const size_t smem = exact ? assign_bytes(KB) : km_smem_bytes(DP, KB, nw), smem_stats = nblocks == 1 ? stats_bytes(KB) : km_stats_smem_bytes(d, KB);
     auto* km = new mlb_km;
     km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->SV = km_sv(d, KP);
     km->KB = KB; km->nblocks = nblocks;
-    km->fn = km_kernel_for<false>(DP);
-    km->fn_compact = km_kernel_for<true>(DP);
+    km->exact = exact;
+    km->nw = nw;
+    km->fn = exact ? km_assign_exact_kernel<false> : km_kernel_for<false>(DP, nw);
+    km->fn_compact = exact ? km_assign_exact_kernel<true> : km_kernel_for<true>(DP, nw);
     km->stats_small = nblocks == 1 && KP == kKmGroup && DP <= 32;   // K <= 32: one-hot tensor-pipe statistics (its accumulators fit the registers up to D = 32)
     km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : nblocks == 1 ? km_stats_kernel_for<false>(DP) : km_stats_kernel_for<true>(DP);
     km->smem = smem;
@@ -889,7 +1029,7 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn_compact), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int per_sm = 0, sms = 0;
-        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn), kKmThreads, smem));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn), exact ? kKmExactTile : nw * 32, smem));
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means kernel does not fit on an SM");
         kg.grid = per_sm * sms;

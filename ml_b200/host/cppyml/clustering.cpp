@@ -17,6 +17,7 @@
 #include "ML/Distributed.hpp"
 #include "ML/EM.hpp"
 #include "ML/KMeans.hpp"
+#include "../src/Backend.hpp"
 
 namespace py = pybind11;
 
@@ -259,6 +260,19 @@ void init_clustering(py::module_& m)
 		.def("assign_labels", &ml::Clustering::KMeansPy::assign_labels_py, py::arg("data").noconvert(),
 			"Assigns every row of data to its closest cluster (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    Tuple of the array of cluster labels and the array of squared Euclidean distances to the cluster centroids.")
 		.doc() = "Lloyd's K-means on B200 GPUs.";
+
+	m.def("_standardise_features", [](const py::array& features) {
+		// (N, D) row-major in, (N, D) row-major out: the same memory as the D x N column-major matrices of the C++ side
+		const auto columns = as_columns(features);
+		Eigen::MatrixXd result;
+		{
+			py::gil_scoped_release release;
+			result = ml::detail::standardise_features(columns);
+		}
+		py::array_t<double> out({result.cols(), result.rows()});
+		std::memcpy(out.mutable_data(), result.data(), sizeof(double) * static_cast<size_t>(result.size()));
+		return out;
+	}, py::arg("features").noconvert(), "Device part of cppyml.utils.standardise_features.");
 
 	auto m_distributed = m.def_submodule("distributed", "One process per GPU: every rank fits its own rows, parameters are exchanged over NCCL (an addition to the reference).");
 	m_distributed.def("unique_id", []() {

@@ -6,3 +6,4 @@ Mirrors the package layout of the reference (cppyml/cppyml/__init__.py:18-21): t
 from .cppyml import clustering  # noqa: F401
 from .cppyml import distributed  # noqa: F401
 from .cppyml import __version__, backend  # noqa: F401
+from . import utils  # noqa: F401,E402

@@ -27,15 +27,12 @@ namespace ml
 
 		namespace
 		{
+			/** The process-wide context is never destroyed: models (static objects of the application, Python objects
+			collected at interpreter shutdown) may outlive any static of this library, and their destructors still need
+			it.  The driver reclaims the device resources when the process ends. */
 			struct ContextHolder
 			{
 				mlb_ctx* ctx = nullptr;
-				~ContextHolder()
-				{
-					if (ctx) {
-						mlb_ctx_destroy(ctx);
-					}
-				}
 			};
 		}
 
@@ -68,6 +65,15 @@ namespace ml
 				check(mlb_ctx_create(nullptr, number_devices, &holder.ctx), "ML++ B200 backend");
 			}
 			return holder.ctx;
+		}
+
+		Eigen::MatrixXd standardise_features(Eigen::Ref<const Eigen::MatrixXd> data)
+		{
+			Eigen::MatrixXd result(data.rows(), data.cols());
+			if (data.size()) {
+				check(mlb_standardise_features(shared_context(), data.data(), data.cols(), static_cast<int>(data.rows()), data.outerStride(), result.data(), data.rows()), "standardise_features");
+			}
+			return result;
 		}
 
 		DeviceData::DeviceData(Eigen::Ref<const Eigen::MatrixXd> data)

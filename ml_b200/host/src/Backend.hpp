@@ -6,6 +6,7 @@
 #include <random>
 #include <vector>
 #include <Eigen/Core>
+#include "ML/dll.hpp"
 
 extern "C" {
 #include "mlb200.h"
@@ -22,6 +23,10 @@ namespace ml
 		default 1).  Created on first use; there is no CPU fallback, so a machine without a CUDA device
 		gets a std::runtime_error from the first fit(). */
 		mlb_ctx* shared_context();
+
+		/** cppyml.utils.standardise_features (cppyml/cppyml/utils.py:8-28) on the device: every row of the D x N matrix
+		minus its mean and, for N > 1, divided by its biased standard deviation. */
+		DLL_DECLSPEC Eigen::MatrixXd standardise_features(Eigen::Ref<const Eigen::MatrixXd> data);
 
 		/** The point matrix in HBM. */
 		class DeviceData

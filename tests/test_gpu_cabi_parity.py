@@ -30,11 +30,14 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / scale)
 
 
-def em_fit_cabi(ctx, data, k, initial_means_dk, *, absolute_tolerance=1e-8, relative_tolerance=1e-8, maximum_steps=1000):
-    """EM::fit's loop (ML/EM.cpp:127-170) on the C-ABI: host convergence test, device steps."""
+def em_fit_cabi(ctx, data, k, initial_means_dk, *, absolute_tolerance=1e-8, relative_tolerance=1e-8, maximum_steps=1000, force_path=0):
+    """EM::fit's loop (ML/EM.cpp:127-170) on the C-ABI: host convergence test, device steps.
+    force_path=3 runs every step on the direct-difference kernels."""
     from ml_b200 import cabi
     d_data = cabi.Data.upload(ctx, data)
     em = cabi.Em(d_data, k)
+    if force_path:
+        em.force_path(force_path)
     cov = em.sample_covariance()
     em.set_params(initial_means_dk, np.repeat(cov[None], k, axis=0), np.full(k, 1.0 / k))
     old = -np.inf
@@ -42,8 +45,10 @@ def em_fit_cabi(ctx, data, k, initial_means_dk, *, absolute_tolerance=1e-8, rela
     out.converged = False
     out.iterations = 0
     out.sample_covariance = cov
+    out.paths = []
     for step in range(maximum_steps):
         ll = em.step()
+        out.paths.append(em.last_path)
         out.iterations = step + 1
         out.log_likelihood = ll
         if step > 0 and abs(ll - old) < absolute_tolerance + relative_tolerance * max(abs(old), abs(ll)):
