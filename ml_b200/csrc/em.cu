@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(kEmThreads, (DP * KP <= 128 || MODE == 2) ? ML
                     }
                     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    const double inv = 1.0 / sum;
+                    const double inv = reciprocal_of_sum(sum);
                     if (c == 0 && pl < nvalid) {
                         ll_acc += mx;
                         ll_prod *= sum;

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kDrThreads) em_direct_e_kernel(const EmDirectA
 #pragma unroll
             for (int off = 8; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
             if (live) {
-                const double inv = 1.0 / sum;
+                const double inv = reciprocal_of_sum(sum);
                 for (int kk = hl; kk < p.KPr; kk += 16) rrow[kk] = exp_nonpositive(__ldcg(rrow + kk) - mx, etab) * inv;   // padding: exp(-inf) = 0
                 if (hl == 0) {
                     ll_acc += mx;
@@ -240,8 +240,8 @@ __global__ void em_direct_ll_kernel(const EmDirectArgs p)
 __global__ void __launch_bounds__(kDrThreads) em_direct_m_kernel(const EmDirectArgs p)
 {
     extern __shared__ __align__(16) double sm[];
-    const int DP = p.DP, NB = DP / 8, WS = DP + 12, WSZ = kDrSub * WS, IMG = dr_img_len(DP), SPC = dr_steps(NB), d = p.d;
-    const int T = dr_tiles(NB), L = dr_stat_len(DP), XSZ = kDrSub * (d + (d & 1)), RSZ = kDrSub * p.cg;
+    const int DP = p.DP, NB = DP / 8, WS = DP + 12, WSZ = kDrSub * WS, IMG = dr_img_len(DP), SPC = dr_steps(NB), d = p.d, cg = p.cg;
+    const int T = dr_tiles(NB), L = dr_stat_len(DP), XSZ = kDrSub * (d + (d & 1)), RSZ = kDrSub * cg;
     double* W = sm;                                    // [cg][16][WS]: w = z - delta_k | 1 | zeros
     double* RW = W + static_cast<size_t>(p.cg) * WSZ;  // [cg + 1][16][WS]: r_ik times the same; the last block is all zeros
     double* dl = RW + static_cast<size_t>(p.cg + 1) * WSZ; // [cg][DP]
@@ -294,27 +294,38 @@ __global__ void __launch_bounds__(kDrThreads) em_direct_m_kernel(const EmDirectA
         const long long p_begin = p.sc_begin[sc], p_end = p.sc_begin[sc + 1];
         const int nsubs = static_cast<int>((p_end - p_begin + kDrSub - 1) / kDrSub);
         auto sub_valid = [&](int s) { const long long left = p_end - (p_begin + static_cast<long long>(s) * kDrSub); return static_cast<int>(left < kDrSub ? left : kDrSub); };
-        // asynchronous copy of sub-tile s: its coordinates (one contiguous run) and its cg responsibilities per point
+        // asynchronous copy of sub-tile s: its coordinates (one contiguous run) and its cg responsibilities per point;
+        // rows past the end of the super-chunk get zero coordinates and zero responsibilities (r = 0 removes them from
+        // every product, and 0 * w must not meet an Inf or NaN left behind in the buffer)
         auto prefetch = [&](int s, int which) {
             const long long sub0 = p_begin + static_cast<long long>(s) * kDrSub;
             const int nv = sub_valid(s), nel = nv * d;
             const double* xg = p.x + sub0 * d;
             double* xs = Xs + which * XSZ;
             if ((d & 1) == 0) {
-                for (int e2 = tid; 2 * e2 < nel; e2 += kDrThreads) sp_cp_async16(xs + 2 * e2, xg + 2 * e2);
+                for (int e2 = tid; 2 * e2 < kDrSub * d; e2 += kDrThreads) {
+                    if (2 * e2 < nel) sp_cp_async16(xs + 2 * e2, xg + 2 * e2);
+                    else *reinterpret_cast<double2*>(xs + 2 * e2) = make_double2(0.0, 0.0);
+                }
             } else {
-                for (int e = tid; e < nel; e += kDrThreads) sp_cp_async8(xs + e, xg + e);
+                for (int e = tid; e < kDrSub * d; e += kDrThreads) {
+                    if (e < nel) sp_cp_async8(xs + e, xg + e);
+                    else xs[e] = 0.0;
+                }
             }
-            if (!p.unit_r) {
-                double* rs = Rs + which * RSZ;
-                for (int pt = warp; pt < nv; pt += 4)
-                    for (int cl = lane; cl < nc; cl += 32) sp_cp_async8(rs + pt * p.cg + cl, p.r + (sub0 + pt) * p.KPr + k0 + cl);
-            }
+            double* rs = Rs + which * RSZ;
+            for (int pt = warp; pt < kDrSub; pt += 4)
+                for (int cl = lane; cl < nc; cl += 32) {
+                    if (p.unit_r) rs[pt * cg + cl] = (pt < nv && k0 + cl == 0) ? 1.0 : 0.0;
+                    else if (pt < nv) sp_cp_async8(rs + pt * cg + cl, p.r + (sub0 + pt) * p.KPr + k0 + cl);
+                    else rs[pt * cg + cl] = 0.0;
+                }
             sp_cp_async_commit();
         };
         if (nsubs > 0) prefetch(0, 0);
+        const int CW = DP + 8;                 // coordinates of an augmented row: w | 1 | zeros
+        const FastDiv by_cw(CW);
         for (int s = 0; s < nsubs; ++s) {
-            const int nv = sub_valid(s);
             if (s + 1 < nsubs) {
                 prefetch(s + 1, (s + 1) & 1);
                 sp_cp_async_wait<1>();
@@ -324,20 +335,21 @@ __global__ void __launch_bounds__(kDrThreads) em_direct_m_kernel(const EmDirectA
             __syncthreads();   // sub-tile s has arrived; every warp is past the products of sub-tile s - 1 (first pass: dl, sh)
             const double* xs = Xs + (s & 1) * XSZ;
             const double* rs = Rs + (s & 1) * RSZ;
-            // w and r w of every (component, point) row: one row per warp at a time, the lanes over the coordinates
-            for (int row = warp; row < nc * kDrSub; row += 4) {
-                const int cl = row >> 4, pt = row & 15;
-                const bool live = pt < nv;
-                double r = 0.0;
-                if (live) r = p.unit_r ? (k0 + cl == 0 ? 1.0 : 0.0) : rs[pt * p.cg + cl];
-                double* wrow = W + cl * WSZ + pt * WS;
-                double* rwrow = RW + cl * WSZ + pt * WS;
-                for (int co = lane; co < DP + 8; co += 32) {
-                    double w = 0.0;
-                    if (co < d) w = live ? (xs[pt * d + co] - sh[co]) - dl[cl * DP + co] : 0.0;
-                    else if (co == DP) w = 1.0;
-                    wrow[co] = w;
-                    rwrow[co] = r * w;
+            // w and r w: a thread takes one (point, coordinate) cell at a time and walks the components, so that the point's
+            // coordinate is read and shifted once and the inner loop is two loads, two FP64 operations and two stores
+            for (int q = tid; q < kDrSub * CW; q += kDrThreads) {
+                const int pt = by_cw.div(q), co = q - pt * CW;
+                const bool coord = co < d;
+                const double z = coord ? xs[pt * d + co] - sh[co] : (co == DP ? 1.0 : 0.0);
+                const double* dlp = dl + (coord ? co : 0);
+                const double* rp = rs + pt * cg;
+                double* wp = W + pt * WS + co;
+                double* rwp = RW + pt * WS + co;
+#pragma unroll 2
+                for (int cl = 0; cl < nc; ++cl) {
+                    const double w = coord ? z - dlp[cl * DP] : z;
+                    wp[cl * WSZ] = w;
+                    rwp[cl * WSZ] = rp[cl] * w;
                 }
             }
             __syncthreads();

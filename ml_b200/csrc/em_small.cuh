@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
                     }
                     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    const double inv = 1.0 / sum;
+                    const double inv = reciprocal_of_sum(sum);
                     if (c == 0 && pl < nvalid) {
                         ll_acc += mx;
                         ll_prod *= sum;

@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) em_split_e_kernel(const EmSplit
                 }
 #pragma unroll
                 for (int off = 8; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-                const double inv = 1.0 / sum;
+                const double inv = reciprocal_of_sum(sum);
                 if (pl < nvalid) {
                     double* rrow = p.r + (tile0 + pl) * KP;
                     for (int kk = hl; kk < KP; kk += 16) rrow[kk] = qrow[kk] * inv;

@@ -106,6 +106,11 @@ namespace ml
 
 		/** Iterations (E-step + M-step pairs) executed by the last fit. */
 		unsigned int number_iterations() const { return number_iterations_; }
+
+		/** Frees the HBM-resident state of the last fit (the points, 8 D bytes each, stay on the device after fit() so that
+		responsibilities(), labels() and the batched assign_responsibilities() can be served).  `keep_results`: bring the
+		pending responsibilities and labels to the host first.  The batched prediction needs a new fit afterwards. */
+		DLL_DECLSPEC void release_device(bool keep_results = true);
 	private:
 		Prng prng_;
 		std::shared_ptr<const Clustering::CentroidsInitialiser> means_initialiser_;

@@ -66,6 +66,10 @@ namespace ml
 
             /** Assignment steps executed by the last (single-initialisation) fit. */
             unsigned int number_iterations() const { return number_iterations_; }
+
+            /** Frees the HBM-resident state of the last fit (the points stay on the device after fit() so that labels()
+            and assign_labels() can be served).  `keep_results`: bring the pending labels to the host first. */
+            DLL_DECLSPEC void release_device(bool keep_results = true);
         private:
             mutable std::vector<unsigned int> labels_;
             mutable bool labels_on_host_;

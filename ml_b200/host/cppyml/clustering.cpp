@@ -234,6 +234,7 @@ void init_clustering(py::module_& m)
 			"Args:\n    k: component index in [0, K).\n\nReturns:\n    The (D, D) covariance of that component.")
 		.def("assign_responsibilities", &ml::EMPy::calculate_responsibilities, py::arg("x"),
 			"Args:\n    x: one point, D values.\n\nReturns:\n    The K responsibilities of the fitted components for x.")
+		.def("release_device", &ml::EMPy::release_device, py::arg("keep_results") = true, "Frees the GPU memory the last fit still holds (the points and the pending results); with keep_results the responsibilities and labels are brought to the host first.")
 		.def("assign_responsibilities_batch", &ml::EMPy::calculate_responsibilities_batch, py::arg("data").noconvert(),
 			"Responsibilities of the fitted components for every row of data (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    2D array, one row of responsibilities per data point.")
 		.doc() = "Full-covariance Gaussian mixture fitted by expectation-maximisation on B200 GPUs.";
@@ -257,6 +258,7 @@ void init_clustering(py::module_& m)
 		.def_property_readonly("number_iterations", &ml::Clustering::KMeansPy::number_iterations, "Assignment steps run by the last fit.")
 		.def("assign_label", &ml::Clustering::KMeansPy::assign_label_py, py::arg("x"),
 			"Args:\n    x: one point, D values.\n\nReturns:\n    (index of the nearest centroid, squared distance to it).")
+		.def("release_device", &ml::Clustering::KMeansPy::release_device, py::arg("keep_results") = true, "Frees the GPU memory the last fit still holds; with keep_results the labels are brought to the host first.")
 		.def("assign_labels", &ml::Clustering::KMeansPy::assign_labels_py, py::arg("data").noconvert(),
 			"Assigns every row of data to its closest cluster (computed on the GPU).\n\nArgs:\n    data: A 2D float64 C-contiguous array with data points in rows.\n\nReturns:\n    Tuple of the array of cluster labels and the array of squared Euclidean distances to the cluster centroids.")
 		.doc() = "Lloyd's K-means on B200 GPUs.";

@@ -118,6 +118,17 @@ namespace ml
 		return labels_;
 	}
 
+	void EM::release_device(bool keep_results)
+	{
+		if (keep_results) {
+			responsibilities();
+			labels();
+		}
+		responsibilities_on_host_ = true;
+		labels_on_host_ = true;
+		device_.reset();
+	}
+
 	bool EM::fit(const DataView data)
 	{
 		converged_ = false;

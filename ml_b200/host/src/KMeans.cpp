@@ -43,6 +43,15 @@ namespace ml
 			return labels_;
 		}
 
+		void KMeans::release_device(bool keep_results)
+		{
+			if (keep_results) {
+				labels();
+			}
+			labels_on_host_ = true;
+			device_.reset();
+		}
+
 		bool KMeans::fit(DataView data)
 		{
 			const auto number_dimensions = static_cast<unsigned int>(data.rows());

@@ -134,3 +134,22 @@ def test_kmeans_on_shared_data_does_not_disturb_a_graphed_em():
         assert np.array_equal(a, b)
     data.close()
     ctx.close()
+
+
+def test_release_device_keeps_the_results(cppyml):
+    data, _, _ = synthetic_gmm(8000, 4, 3, seed=9, spread=8.0)
+    em = cppyml.clustering.EM(3)
+    em.set_seed(3)
+    em.fit(data)
+    ref = oracle.em_fit(data, 3, seed=3)
+    em.release_device()
+    assert np.max(np.abs(em.responsibilities - ref.responsibilities)) <= 1e-9
+    assert np.array_equal(em.labels_array, ref.labels)
+    with pytest.raises(Exception):
+        em.assign_responsibilities_batch(data[:10])
+    km = cppyml.clustering.KMeans(3)
+    km.set_seed(3)
+    km.fit(data)
+    kref = oracle.kmeans_fit(data, 3, seed=3)
+    km.release_device()
+    assert np.array_equal(km.labels_array, kref.labels)
