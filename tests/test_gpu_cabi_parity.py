@@ -127,16 +127,42 @@ def test_em_full_fit_matches_oracle(ctx, n, d, k, seed):
 
 
 def test_em_mouse_c1_matches_oracle(ctx):
-    """BASELINE config 1: mouse data, N=10k, D=2, K=3, KPP-initialised means, tolerance 1e-14 (Benchmarks/bm_EM.cpp:9-48)."""
+    """BASELINE config 1: mouse data, N=10k, D=2, K=3, KPP-initialised means, tolerance 1e-14 (Benchmarks/bm_EM.cpp:9-48).
+
+    At a 1e-14 tolerance the stopping step is decided by the 16th digit of the log-likelihood: the fit converges
+    linearly (about 130 iterations), so |ll_t - ll_(t-1)| creeps towards the threshold 1e-14 + 1e-14 |ll| = 2.5e-14, which is
+    ~100 ulp of ll, over many steps, and a difference of a few ulp between two correct evaluations of ll moves the crossing
+    by a few steps.  The test therefore (a) demands bitwise-level agreement where the comparison is well posed: the first
+    100 iterations of the trace against a fixed-step oracle run, and (b) SHOWS that the two stopping steps differ only
+    inside that plateau: at every step between them our own |delta ll| is within a factor 3 of the threshold."""
+    from ml_b200 import cabi
     data, _ = oracle.testdata_mouse(10000)
     init = oracle.centroids_init(oracle.KPP, data, 3, seed=42)
     ref = oracle.em_fit(data, 3, means_init=oracle.EXPLICIT, explicit_means=init, absolute_tolerance=1e-14, relative_tolerance=1e-14)
     got = em_fit_cabi(ctx, data, 3, init, absolute_tolerance=1e-14, relative_tolerance=1e-14)
-    # at a 1e-14 tolerance the stopping step is decided by rounding noise, so the count may differ by a few steps
     assert got.converged and ref.converged
-    assert abs(got.iterations - ref.iterations) <= max(5, ref.iterations // 20)
+    # (a) a well-posed comparison: 100 iterations from the same start, no stopping rule involved
+    ref100 = oracle.em_fit(data, 3, means_init=oracle.EXPLICIT, explicit_means=init, absolute_tolerance=0.0, relative_tolerance=0.0, maximum_steps=100)
+    got100 = em_fit_cabi(ctx, data, 3, init, absolute_tolerance=0.0, relative_tolerance=0.0, maximum_steps=100)
+    assert abs(got100.log_likelihood - ref100.log_likelihood) <= RTOL * abs(ref100.log_likelihood)
+    assert rel_err(got100.means, ref100.means) <= RTOL and rel_err(got100.covariances, ref100.covariances) <= RTOL
+    assert rel_err(got100.mixing_probabilities, ref100.mixing_probabilities) <= RTOL
+    assert np.max(np.abs(got100.responsibilities - ref100.responsibilities)) <= RTOL
+    # (b) the stopping steps: our own trace between the two
+    lo, hi = sorted((got.iterations, ref.iterations))
+    dev = cabi.Data.upload(ctx, data)
+    em = cabi.Em(dev, 3)
+    cov = em.sample_covariance()
+    em.set_params(init, np.repeat(cov[None], 3, axis=0), np.full(3, 1.0 / 3))
+    trace = em.run_steps(hi + 1)
+    em.close(); dev.close()
+    threshold = 1e-14 + 1e-14 * abs(trace[-1])
+    for t in range(lo - 1, hi):
+        change = abs(trace[t] - trace[t - 1])
+        assert change <= 3 * threshold, (t, change, threshold)
+    assert hi - lo <= max(5, ref.iterations // 20), (got.iterations, ref.iterations)
     assert abs(got.log_likelihood - ref.log_likelihood) <= RTOL * abs(ref.log_likelihood)
-    assert rel_err(got.means, ref.means) <= 1e-7
+    assert rel_err(got.means, ref.means) <= 1e-7          # both stopped on the plateau, a few (slowly converging) steps apart
     assert np.mean(got.labels != ref.labels) <= 1e-3
 
 
