@@ -66,6 +66,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--points", type=int, default=0, help="override the workload's total point count (developer runs)")
+    ap.add_argument("--no-clocks", action="store_true", help="developer runs: no NVML clock sampling thread")
     ap.add_argument("--cpu-sample", type=int, default=0, help="points of the CPU sample (0 = fit --cpu-budget)")
     ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the baseline (0 = 25 s in cpu_baseline, 150 s in --impl reference)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -519,11 +520,12 @@ def main():
         gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         gpu_uuid = None
-    clocks = ClockSampler(local_rank, gpu_uuid)
-    if rank == 0:
+    clocks = ClockSampler(local_rank, gpu_uuid)   # every rank samples its own GPU: a straggler GPU sets the max-over-ranks time
+    if not args.no_clocks:
         clocks.start()
     warm_trace = run.run(args.warmup, True)
     launches0 = run.obj.launch_count
+    direct0 = run.obj.direct_steps if kind == "em" else 0
     run.obj.set_kernel_timing(True)
     barrier()
     clocks.mark_begin()
@@ -535,11 +537,29 @@ def main():
     kernel_ms, kernel_launches = run.obj.kernel_time_ms()
     run.obj.set_kernel_timing(False)
     launches = run.obj.launch_count - launches0
-    clock_info = clocks.stop() if rank == 0 else None
+    direct_steps = run.obj.direct_steps - direct0 if kind == "em" else 0
+    clock_info = clocks.stop()
+    my_ms_total = ms_total
     ms_total = max_over_ranks(ms_total)
     ms_per_step = ms_total / args.steps
     value = n_total * k / (ms_per_step * 1e-3) / 1e9
     kernel_ms_avg = max_over_ranks(kernel_ms / max(1, kernel_launches))
+    per_rank = None
+    if world > 1:
+        mine = {"rank": rank, "ms_per_step": my_ms_total / args.steps, "kernel_ms_avg": kernel_ms / max(1, kernel_launches), "points": n_local,
+                "sm_mhz": clock_info.get("sm_mhz"), "sm_mhz_min": clock_info.get("sm_mhz_min"), "power_w_max": clock_info.get("power_w_max"),
+                "reasons": clock_info.get("reasons")}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        per_rank = gathered
+        if rank == 0:
+            # the line's clocks are the worst rank's: lowest median SM clock, all reasons seen anywhere
+            worst = min((g for g in gathered if g["sm_mhz"] is not None), key=lambda g: g["sm_mhz"], default=None)
+            if worst is not None:
+                clock_info = dict(clock_info, sm_mhz=worst["sm_mhz"], sm_mhz_min=min(g["sm_mhz_min"] for g in gathered if g["sm_mhz_min"] is not None),
+                                  power_w_max=max(g["power_w_max"] for g in gathered if g["power_w_max"] is not None),
+                                  reasons=sorted({r for g in gathered for r in (g["reasons"] or [])}),
+                                  note=clock_info.get("note", "") + "; every rank sampled its own GPU, sm_mhz is the lowest median over the ranks (per_rank has each)")
     full_trace = np.concatenate([np.asarray(warm_trace, dtype=np.float64), np.asarray(trace, dtype=np.float64)])
 
     # ---- e2e: the plugin call.  cppyml.clustering.EM(k).fit(X) / KMeans(k).fit(X) on a plain pageable numpy array (this
@@ -642,7 +662,9 @@ def main():
             "roofline": {"bound": "tensor", "pipe": "FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64); shares the SM's FP64 unit with DFMA",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_source,
                          "dmma_peak_tflops": dmma_peak, "dfma_peak_tflops": dfma_peak,
-                         "kernel": Runner.kernel, "kernel_ms_avg": kernel_ms_avg, "kernel_launches_timed": kernel_launches,
+                         "kernel": Runner.kernel + (f"; {direct_steps} of the {args.steps} timed steps were routed to the direct-difference kernels (kappa > 3e5)"
+                                                    if kind == "em" else ""),
+                         "timed_steps_on_direct_kernels": direct_steps, "kernel_ms_avg": kernel_ms_avg, "kernel_launches_timed": kernel_launches,
                          "flops_per_launch": flops_per_launch,
                          "flops_per_point_component": f_em(d) if kind == "em" else 3 * d + 1,
                          "hbm_achieved_gbs": hbm_gbs, "hbm_peak_gbs": hbm_peak, "hbm_frac": hbm_gbs / hbm_peak,
@@ -658,6 +680,8 @@ def main():
                 if entry is not None:
                     line["roofline"]["traffic"] = entry
                     break
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:

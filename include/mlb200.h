@@ -210,13 +210,15 @@ int mlb_em_kernel_time_ms(mlb_em* em, double* total_ms, int64_t* launches);
 /* Which device path the last step used: 1 = fused DMMA E+M kernel, 2 = split E / M kernels (both in feature space
  * about the data mean), 3 = direct-difference E / M kernels (per-component centring, as EM.cpp:205-207,246-248). */
 int mlb_em_last_path(const mlb_em* em, int* path);
+/* How many steps of this object took the direct-difference kernels so far (bench.py reports it next to its timings). */
+int mlb_em_direct_steps(const mlb_em* em, int64_t* steps);
 
 /* Numerical domain of the feature-space kernels and the routing between the paths.  The feature-space kernels expand
  * the quadratic form about ONE shift c (the data mean); their error grows with kappa = max_k (mu_k - c)^T P_k (mu_k - c),
  * the squared distance of a component from the centre of the data in its own standard deviations (relative error
  * ~1e-16 kappa: 1e-13 for standardised data, 1e-8 for tight clusters 1e4 standard deviations apart).  The library
  * computes kappa with every parameter refresh and runs the next step on the direct-difference kernels whenever
- * kappa > 3e4, when D > 64 or K > 256 (shapes only those kernels take), or when forced.  Guaranteed domain: results
+ * kappa > 3e5 (about 1.5e-11 lost to cancellation), when D > 64 or K > 256 (shapes only those kernels take), or when forced.  Guaranteed domain: results
  * within 1e-9 of the reference wherever the reference itself is finite, for any K and D <= 128.
  * mlb_em_force_path: path = 3 always uses the direct kernels, 0 restores the automatic choice.
  * mlb_em_conditioning: kappa of the current parameters and the path the next step will take. */
@@ -259,6 +261,29 @@ int mlb_km_launch_count(const mlb_km* km, int64_t* launches);
 /* As mlb_em_set_kernel_timing / mlb_em_kernel_time_ms, for the assignment kernel. */
 int mlb_km_set_kernel_timing(mlb_km* km, int enabled);
 int mlb_km_kernel_time_ms(mlb_km* km, double* total_ms, int64_t* launches);
+
+/* ---------------------------------------------------------------- K-means start sets (KMeans::fit with number_initialisations_ > 1,
+ * ML/KMeans.cpp:29-47; the 3-start fit of Benchmarks/bm_KMeans.cpp:39-45)
+ *
+ * The reference runs the starts of a multi-start fit one after the other.  An mlb_kms holds up to 4 starts ("sets": K centroids,
+ * N labels, statistics each) on one resident data set and advances them in lockstep: one pass of the assignment kernel reads
+ * every point once and scores it against all active sets, one reduction / exchange and one read-back serve all of them.  Per
+ * set, labels, inertia, changed counts and centroids are bit for bit those of an mlb_km driven through the same calls.
+ * `active` is a bit mask of the sets a call advances (bit s = set s); a start that has converged is simply left out of it. */
+typedef struct mlb_kms mlb_kms;
+/* 1 when n_sets (1..4) sets of k centroids fit one CTA's shared memory at this data's D (D <= 64), else 0: the caller then
+ * runs the starts one at a time on an mlb_km (same results). */
+int mlb_kms_supported(const mlb_data* data, int k, int n_sets);
+int mlb_kms_create(mlb_ctx* ctx, mlb_data* data, int k, int n_sets, mlb_kms** out);
+int mlb_kms_destroy(mlb_kms* kms);
+int mlb_kms_set_centroids(mlb_kms* kms, int set, const double* centroids /* D x K */);
+int mlb_kms_get_centroids(mlb_kms* kms, int set, double* centroids /* D x K */);
+/* mlb_km_assign for every active set: inertia[s], n_changed[s] are written for active sets only (arrays of n_sets). */
+int mlb_kms_assign(mlb_kms* kms, unsigned int active, double* inertia, int64_t* n_changed);
+/* mlb_km_update for every active set: centroid_shift_sq[s] for active sets only. */
+int mlb_kms_update(mlb_kms* kms, unsigned int active, double* centroid_shift_sq);
+int mlb_kms_get_labels(mlb_kms* kms, int set, unsigned int* labels);
+int mlb_kms_launch_count(const mlb_kms* kms, int64_t* launches);
 
 #ifdef __cplusplus
 }

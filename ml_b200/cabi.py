@@ -69,6 +69,7 @@ SIGNATURES = {
     "mlb_em_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "mlb_em_kernel_time_ms": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
     "mlb_em_last_path": (ctypes.c_int, [_vp, _c_ip]),
+    "mlb_em_direct_steps": (ctypes.c_int, [_vp, _c_i64p]),
     "mlb_em_force_path": (ctypes.c_int, [_vp, ctypes.c_int]),
     "mlb_em_conditioning": (ctypes.c_int, [_vp, _c_dp, _c_ip]),
     "mlb_em_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
@@ -83,6 +84,15 @@ SIGNATURES = {
     "mlb_km_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
     "mlb_km_set_kernel_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "mlb_km_kernel_time_ms": (ctypes.c_int, [_vp, _c_dp, _c_i64p]),
+    "mlb_kms_supported": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int]),
+    "mlb_kms_create": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "mlb_kms_destroy": (ctypes.c_int, [_vp]),
+    "mlb_kms_set_centroids": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "mlb_kms_get_centroids": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "mlb_kms_assign": (ctypes.c_int, [_vp, ctypes.c_uint, _c_dp, _c_i64p]),
+    "mlb_kms_update": (ctypes.c_int, [_vp, ctypes.c_uint, _c_dp]),
+    "mlb_kms_get_labels": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "mlb_kms_launch_count": (ctypes.c_int, [_vp, _c_i64p]),
 }
 
 _lib = None
@@ -396,6 +406,12 @@ class Em:
         check(lib().mlb_em_last_path(self._h, ctypes.byref(p)))
         return p.value
 
+    @property
+    def direct_steps(self):
+        n = ctypes.c_int64()
+        check(lib().mlb_em_direct_steps(self._h, ctypes.byref(n)))
+        return n.value
+
     def force_path(self, path):
         """3: always the direct-difference kernels; 0: automatic routing."""
         check(lib().mlb_em_force_path(self._h, path))
@@ -488,6 +504,69 @@ class Km:
     def close(self):
         if self._h:
             lib().mlb_km_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Kms:
+    """Up to four K-means starts advanced in lockstep on one resident data set (mlb_kms, KMeans.cpp:29-47).  `active` is a
+    bit mask of the starts a call advances (default: all)."""
+
+    def __init__(self, data, k, n_sets):
+        self.data, self.k, self.n_sets = data, k, n_sets
+        self.n_total, self.n_local, self.d = data.shape
+        self._h = _vp()
+        check(lib().mlb_kms_create(data.ctx._h, data._h, k, n_sets, ctypes.byref(self._h)))
+        data.ctx._children.add(self)
+
+    @staticmethod
+    def supported(data, k, n_sets):
+        return bool(lib().mlb_kms_supported(data._h, k, n_sets))
+
+    def _mask(self, active):
+        return (1 << self.n_sets) - 1 if active is None else int(active)
+
+    def set_centroids(self, s, centroids_dk):
+        c = np.ascontiguousarray(np.asarray(centroids_dk, dtype=np.float64).T)
+        assert c.shape == (self.k, self.d)
+        check(lib().mlb_kms_set_centroids(self._h, s, _ptr(c)))
+
+    def get_centroids(self, s):
+        c = np.empty((self.k, self.d))
+        check(lib().mlb_kms_get_centroids(self._h, s, _ptr(c)))
+        return c.T.copy()
+
+    def assign(self, active=None):
+        """(inertia[n_sets], changed[n_sets]); entries of starts outside `active` stay 0."""
+        inertia = np.zeros(4)
+        changed = np.zeros(4, dtype=np.int64)
+        check(lib().mlb_kms_assign(self._h, self._mask(active), inertia.ctypes.data_as(_c_dp), changed.ctypes.data_as(_c_i64p)))
+        return inertia[: self.n_sets], changed[: self.n_sets]
+
+    def update(self, active=None):
+        shift = np.zeros(4)
+        check(lib().mlb_kms_update(self._h, self._mask(active), shift.ctypes.data_as(_c_dp)))
+        return shift[: self.n_sets]
+
+    def get_labels(self, s):
+        labels = np.empty(self.n_local, dtype=np.uint32)
+        check(lib().mlb_kms_get_labels(self._h, s, _ptr(labels)))
+        return labels
+
+    @property
+    def launch_count(self):
+        c = ctypes.c_int64()
+        check(lib().mlb_kms_launch_count(self._h, ctypes.byref(c)))
+        return c.value
+
+    def close(self):
+        if self._h:
+            lib().mlb_kms_destroy(self._h)
             self._h = _vp()
 
     def __del__(self):

@@ -44,6 +44,13 @@ struct KmArgs {
     double* dist_out;       // optional: the squared distance of every point to its centroid (mlb_km_predict, centroid blocks)
     int pstride;            // statistics: doubles between the partial vectors of consecutive chunks
     int k_lo;               // statistics: first cluster of the block this launch accumulates (KP clusters from k_lo)
+    int stat_off;           // statistics: extra offset (doubles) of this launch's K x (D+1) block inside a chunk's partial vector (start sets)
+    // start sets (km_assign_kernel<..., MULTI = true>, mlb_kms): n_sets centroid sets of k centroids each against the same
+    // points in one pass.  cfrag is [n_sets][DP * KP], cnorm [n_sets][KP], craw [n_sets][D x K], cmax [n_sets], labels
+    // [n_sets][label_stride]; a chunk's partial vector is [n_sets][KP x (D+1)] followed by (inertia, changed) per set.
+    int n_sets;
+    unsigned active;        // bit s: set s takes part in this pass (a converged start is frozen)
+    long long label_stride;
 };
 
 __device__ __forceinline__ void km_dmma(double (&acc)[2], double a, double b)
@@ -57,6 +64,12 @@ __host__ __device__ inline int km_sv(int d, int KP) { return KP * (d + 1) + 8; }
 inline size_t km_smem_bytes(int DP, int KP, int nw = 4)
 {
     return sizeof(double) * (static_cast<size_t>(DP) * KP + KP + 2 * static_cast<size_t>(nw) * 16 * (DP + 4) + DP + 32) + sizeof(int) * 3 * nw * 16;
+}
+// the same with ns centroid sets resident at once and a per-thread (inertia, changed) accumulator per set
+inline size_t km_sets_smem_bytes(int DP, int KP, int nw, int ns)
+{
+    return km_smem_bytes(DP, KP, nw) + sizeof(double) * (static_cast<size_t>(ns - 1) * (static_cast<size_t>(DP) * KP + KP) + static_cast<size_t>(ns) * nw * 32)
+           + sizeof(int) * static_cast<size_t>(ns) * nw * 32;
 }
 inline size_t km_stats_smem_bytes(int d, int KP)
 {
@@ -115,24 +128,39 @@ constexpr int kKmSub = 16;   // points per warp sub-tile
 // D = 32, K = 256: two CTAs of four warps, 8 warps per SM) one wide CTA keeps twice the warps resident on the same image
 // (NW = 16: 4 per sub-partition), which is what hides the fixed issue latency between a warp's DMMAs and the global loads
 // of the refinement (ncu r01j: 36 % of the stall samples were `wait`, 14.5 % long scoreboard, the FP64 pipe 69 % busy).
-template <int DP, bool COMPACT, int NW>
+// MULTI: p.n_sets centroid sets ("starts" of a multi-start fit, KMeans.cpp:29-47) against the same points in one pass: the
+// point sub-tile is staged and turned into A fragments once, then filter + refinement run per set on that set's image,
+// labels and (inertia, changed) accumulators.  Per set the arithmetic and its order are those of the one-set kernel, so a
+// set's labels, inertia and changed count are bit for bit what a fit of that start alone produces.  A template parameter:
+// the one-set instantiations are instruction for instruction the measured ones.
+template <int DP, bool COMPACT, int NW, bool MULTI = false>
 __global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
 {
     constexpr int DQ = DP / 4, XS = DP + 4, kKmTile = NW * 16, kKmThreads = NW * 32;
+    static_assert(!(MULTI && COMPACT), "start sets write full statistics vectors");
     extern __shared__ __align__(16) double sm[];
     const int KP = p.KP, d = p.d, SD = d + 1;
-    double* Bf = sm;                                  // DP * KP
-    double* nrm = Bf + static_cast<size_t>(DP) * KP;  // KP
-    double* Xb = nrm + KP;                            // [4 warps][2 buffers][16][XS], raw coordinates (padding columns zero)
+    const int NS = MULTI ? p.n_sets : 1;
+    double* Bf = sm;                                  // [NS] DP * KP
+    double* nrm = Bf + static_cast<size_t>(NS) * DP * KP;  // [NS] KP
+    double* Xb = nrm + NS * KP;                       // [4 warps][2 buffers][16][XS], raw coordinates (padding columns zero)
     double* sh = Xb + 2 * kKmTile * XS;               // DP
     double* red = sh + DP;                            // 32
     int* labs_all = reinterpret_cast<int*>(red + 32); // [NW][16]: the filter's verdict (~label: ambiguous under its rounding bound)
     unsigned* oldl_all = reinterpret_cast<unsigned*>(labs_all + kKmTile);  // [NW][2][16]: previous labels
+    // MULTI: every thread's running (inertia, changed) of the chunk, per set (the one-set kernel keeps them in registers)
+    double* set_inertia = reinterpret_cast<double*>(oldl_all + 2 * kKmTile);   // [NS][threads]
+    int* set_changed = reinterpret_cast<int*>(set_inertia + (MULTI ? NS * kKmThreads : 0));   // [NS][threads]
     __shared__ int s_next;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
 
-    for (int i = tid; i < DP * KP + KP; i += kKmThreads) sm[i] = i < DP * KP ? p.cfrag[i] : p.cnorm[i - DP * KP];
+    if (MULTI) {
+        for (int i = tid; i < NS * DP * KP; i += kKmThreads) Bf[i] = p.cfrag[i];
+        for (int i = tid; i < NS * KP; i += kKmThreads) nrm[i] = p.cnorm[i];
+    } else {
+        for (int i = tid; i < DP * KP + KP; i += kKmThreads) sm[i] = i < DP * KP ? p.cfrag[i] : p.cnorm[i - DP * KP];
+    }
     for (int i = tid; i < 2 * kKmTile * XS; i += kKmThreads) Xb[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
     __syncthreads();
@@ -140,7 +168,7 @@ __global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
 #pragma unroll
     for (int j = 0; j < DQ; ++j) shc[j] = sh[4 * j + c];
     const double u_bound = 8.0 * (d + 4) * 1.1102230246251565e-16;
-    const double cmax = *p.cmax;
+    const double cmax1 = *p.cmax;
     double* Xw = Xb + warp * (2 * kKmSub * XS);
     int* labs = labs_all + warp * kKmSub;
     unsigned* oldw = oldl_all + warp * (2 * kKmSub);
@@ -181,6 +209,8 @@ __global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
         const int nsubs = static_cast<int>((p_end - p_begin + kKmSub - 1) / kKmSub);
         double inertia_acc = 0.0;
         int changed_acc = 0;
+        if (MULTI)
+            for (int s = 0; s < NS; ++s) { set_inertia[s * kKmThreads + tid] = 0.0; set_changed[s * kKmThreads + tid] = 0; }
 
         // warp w takes the sub-tiles w, w + NW, w + 2 NW, ... of the chunk
         auto sub_begin = [&](int t) { return p_begin + static_cast<long long>(t) * kKmSub; };
@@ -221,13 +251,19 @@ __global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
             // with 20 mantissa bits: three integer min/max, a compare and a select per score instead of IEEE fmin/fmax
             // chains.  What the truncation (and FP64 rounding) cannot separate is sent to the exact scan below.
             const double zz[2] = {zz0, zz1};
+            for (int set = 0; set < NS; ++set) {
+            if (MULTI && !((p.active >> set) & 1u)) continue;
+            const double* Bfs = MULTI ? Bf + static_cast<size_t>(set) * DP * KP : Bf;
+            const double* nrms = MULTI ? nrm + set * KP : nrm;
+            const double* craws = MULTI ? p.craw + static_cast<long long>(set) * d * p.k : p.craw;
+            const double cmax = MULTI ? p.cmax[set] : cmax1;
             int bestk[2] = {0x7fffffff, 0x7fffffff}, secondk[2] = {0x7fffffff, 0x7fffffff};
             int bk[2] = {0, 0};
             for (int grp = 0; grp < KP / kKmGroup; ++grp) {
                 double acc[2][4][2];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
-                    const double2 nn = *reinterpret_cast<const double2*>(nrm + grp * kKmGroup + 8 * nt + 2 * c);
+                    const double2 nn = *reinterpret_cast<const double2*>(nrms + grp * kKmGroup + 8 * nt + 2 * c);
 #pragma unroll
                     for (int mt = 0; mt < 2; ++mt) {
                         acc[mt][nt][0] = nn.x + zz[mt];
@@ -236,7 +272,7 @@ __global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
                 }
 #pragma unroll
                 for (int j = 0; j < DQ; ++j) {
-                    const double2* bp = reinterpret_cast<const double2*>(Bf) + (static_cast<size_t>(j) * (KP / 16) + grp * 2) * 32 + lane;
+                    const double2* bp = reinterpret_cast<const double2*>(Bfs) + (static_cast<size_t>(j) * (KP / 16) + grp * 2) * 32 + lane;
                     const double2 b01 = bp[0], b23 = bp[32];
                     km_dmma(acc[0][0], z0[j], b01.x); km_dmma(acc[1][0], z1[j], b01.x);
                     km_dmma(acc[0][1], z0[j], b01.y); km_dmma(acc[1][1], z1[j], b01.y);
@@ -292,7 +328,7 @@ __global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
                 if (ambiguous) label = ~label;
                 constexpr int HD = DP / 2;
                 double tv[HD];
-                const double* cr = p.craw + static_cast<long long>(label) * d;
+                const double* cr = craws + static_cast<long long>(label) * d;
 #pragma unroll
                 for (int u = 0; u < HD; ++u) tv[u] = l_lo + u < l_hi ? __ldg(cr + l_lo + u) : 0.0;
 #pragma unroll
@@ -316,42 +352,59 @@ __global__ void __launch_bounds__(NW * 32) km_assign_kernel(const KmArgs p)
                     d2 = INFINITY;
                     label = 0;
                     for (int kk = 0; kk < p.k; ++kk) {
-                        const double sq = exact_distance(xr, p.craw + static_cast<long long>(kk) * d, d);
+                        const double sq = exact_distance(xr, craws + static_cast<long long>(kk) * d, d);
                         if (sq < d2) { d2 = sq; label = kk; }
                     }
                 }
                 if (!half && valid) {
-                    inertia_acc += d2;
-                    if (old_labels[pl] != static_cast<unsigned>(label)) ++changed_acc;
-                    p.labels[tile0 + pl] = static_cast<unsigned>(label);
-                    if (COMPACT && p.dist_out) p.dist_out[tile0 + pl] = d2;
+                    if (MULTI) {
+                        unsigned* lab_s = p.labels + static_cast<long long>(set) * p.label_stride + tile0 + pl;
+                        set_inertia[set * kKmThreads + tid] += d2;
+                        if (*lab_s != static_cast<unsigned>(label)) ++set_changed[set * kKmThreads + tid];
+                        *lab_s = static_cast<unsigned>(label);
+                    } else {
+                        inertia_acc += d2;
+                        if (old_labels[pl] != static_cast<unsigned>(label)) ++changed_acc;
+                        p.labels[tile0 + pl] = static_cast<unsigned>(label);
+                        if (COMPACT && p.dist_out) p.dist_out[tile0 + pl] = d2;
+                    }
                 }
             }
-            __syncwarp();   // the buffer and the verdicts are rewritten two sub-tiles later / by the next sub-tile
+            __syncwarp();   // the buffer and the verdicts are rewritten two sub-tiles later / by the next sub-tile / by the next set
+            }   // set
         }
 
         // ---------------- the chunk's inertia and changed-label count: fixed order inside the warp and across the warps
-        double* out = COMPACT ? p.partials + static_cast<long long>(chunk) * 8 - KP * SD : p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        double* out = COMPACT ? p.partials + static_cast<long long>(chunk) * 8 - KP * SD
+                      : MULTI ? p.partials + static_cast<long long>(chunk) * p.pstride + (NS - 1) * KP * SD   // scalars after the NS statistics blocks
+                              : p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        for (int set = 0; set < NS; ++set) {
+            if (MULTI) {
+                inertia_acc = set_inertia[set * kKmThreads + tid];
+                changed_acc = set_changed[set * kKmThreads + tid];
+                __syncthreads();   // red[] of the previous set has been read
+            }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, off);
-            changed_acc += __shfl_xor_sync(0xffffffffu, changed_acc, off);
+            for (int off = 16; off >= 1; off >>= 1) {
+                inertia_acc += __shfl_xor_sync(0xffffffffu, inertia_acc, off);
+                changed_acc += __shfl_xor_sync(0xffffffffu, changed_acc, off);
+            }
+            if (lane == 0) { red[warp] = inertia_acc; red[16 + warp] = static_cast<double>(changed_acc); }
+            __syncthreads();
+            if (tid == 0) {
+                // fixed pairwise tree over the NW warps
+                double a[NW], b[NW];
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { a[w] = red[w]; b[w] = red[16 + w]; }
+#pragma unroll
+                for (int span = 1; span < NW; span <<= 1)
+#pragma unroll
+                    for (int w = 0; w + span < NW; w += 2 * span) { a[w] += a[w + span]; b[w] += b[w + span]; }
+                out[KP * SD + 2 * set] = a[0];
+                out[KP * SD + 2 * set + 1] = b[0];
+            }
         }
-        if (lane == 0) { red[warp] = inertia_acc; red[16 + warp] = static_cast<double>(changed_acc); }
-        __syncthreads();
-        if (tid == 0) {
-            // fixed pairwise tree over the NW warps
-            double a[NW], b[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) { a[w] = red[w]; b[w] = red[16 + w]; }
-#pragma unroll
-            for (int span = 1; span < NW; span <<= 1)
-#pragma unroll
-                for (int w = 0; w + span < NW; w += 2 * span) { a[w] += a[w + span]; b[w] += b[w + span]; }
-            out[KP * SD] = a[0];
-            out[KP * SD + 1] = b[0];
-        }
-        if (tid >= 2 && tid < 8) out[KP * SD + tid] = 0.0;
+        if (tid >= 2 * NS && tid < 8) out[KP * SD + tid] = 0.0;
     }
 }
 
@@ -534,7 +587,7 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
         if (reg_counts && lane < KP / 8) sums[static_cast<size_t>(own_lo + lane) * SD + d] = cnt;
         cnt = 0.0;
         __syncthreads();
-        double* out = BLOCKED ? p.partials + static_cast<long long>(chunk) * p.pstride + static_cast<long long>(p.k_lo) * SD
+        double* out = BLOCKED ? p.partials + static_cast<long long>(chunk) * p.pstride + static_cast<long long>(p.k_lo) * SD + p.stat_off
                               : p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
         for (int i = tid; i < KP * SD; i += kStThreads) {
             out[i] = sums[i];
@@ -641,7 +694,7 @@ __global__ void __launch_bounds__(kKmThreads) km_stats_small_kernel(const KmArgs
             }
         }
         __syncthreads();
-        double* out = p.partials + static_cast<long long>(chunk) * km_sv(d, p.KP);
+        double* out = p.partials + static_cast<long long>(chunk) * (p.pstride ? p.pstride : km_sv(d, p.KP)) + p.stat_off;   // pstride: start sets
         for (int i = tid; i < p.KP * SD; i += kKmThreads) {
             const int kk = i / SD, col = i - kk * SD;
             out[i] = redbuf[kk * (8 * NTD) + col];
@@ -1247,6 +1300,342 @@ int mlb_km_kernel_time_ms(mlb_km* km, double* total_ms, int64_t* launches)
 int mlb_km_launch_count(const mlb_km* km, int64_t* launches)
 {
     MLB_REQUIRE(km && launches, "mlb_km_launch_count: null argument");
+    *launches = km->launches;
+    return MLB_OK;
+}
+
+}  // extern "C"
+
+// ======================================================================= start sets (multi-start K-means, KMeans.cpp:29-47)
+// The reference runs the number_initialisations_ starts of a fit one after the other, each a full Lloyd loop over the data.
+// Here up to kKmsMaxSets starts advance in lockstep: ONE pass of the assignment kernel stages every point sub-tile once and
+// scores it against all the sets' centroid images (km_assign_kernel<..., MULTI>), the per-set statistics land side by side in
+// a chunk's partial vector ([set][K x (D+1)], then (inertia, changed) per set), so one reduction / exchange, one read-back
+// and two host synchronisations per iteration serve all the starts.  A start that has converged is frozen (its bit leaves
+// the active mask: no scoring, no statistics, no update), which is what keeps every start's trajectory the one it has alone.
+
+namespace mlb {
+
+constexpr int kKmsMaxSets = 4;   // the 8 scalar slots of a partial vector hold (inertia, changed) for four sets
+
+template <int NW>
+static KmKernelFn kms_kernel_for_nw(int DP)
+{
+    switch (DP) {
+    case 4: return km_assign_kernel<4, false, NW, true>;
+    case 8: return km_assign_kernel<8, false, NW, true>;
+    case 16: return km_assign_kernel<16, false, NW, true>;
+    case 32: return km_assign_kernel<32, false, NW, true>;
+    case 64: return km_assign_kernel<64, false, NW, true>;
+    default: return nullptr;
+    }
+}
+
+// out[4 s + 1] = inertia of set s, out[4 s + 2] = its changed-label count (the layout mlb_km uses, one group of 4 per set)
+__global__ void kms_scalars_kernel(const double* vsum, int SV, int base, int n_sets, double* out)
+{
+    const int s = threadIdx.x;
+    if (s >= n_sets) return;
+    out[4 * s + 1] = tree8(vsum + base + 2 * s, SV);
+    out[4 * s + 2] = tree8(vsum + base + 2 * s + 1, SV);
+}
+
+struct KmsGpu {
+    double* craw = nullptr;    // [S][D x K]
+    double* cold = nullptr;
+    double* cfrag = nullptr;   // [S][DP * KP]
+    double* cnorm = nullptr;   // [S][KP]
+    double* cmax = nullptr;    // [S]
+    unsigned* labels = nullptr;  // [S][n_local]
+    double* partials = nullptr;  // [n_chunks][SV]
+    double* vsum = nullptr;      // [8][SV]
+    double* out = nullptr;       // [4 S]
+    unsigned* counter = nullptr;
+    int grid = 0, grid_stats = 0;
+};
+
+}  // namespace mlb
+
+struct mlb_kms {
+    mlb_ctx* ctx = nullptr;
+    mlb_data* data = nullptr;
+    int d = 0, k = 0, DP = 0, KP = 0, n_sets = 0, SV = 0, nw = 4;
+    std::vector<mlb::KmsGpu> gpus;
+    mlb::KmKernelFn fn = nullptr, fn_stats = nullptr;
+    bool stats_small = false;
+    size_t smem = 0, smem_stats = 0;
+    unsigned have_centroids = 0, have_stats = 0;   // bit per set
+    int64_t launches = 0;
+    mlb::ReduceScratch reduce_scratch;
+};
+
+namespace mlb {
+
+static int kms_prepare(mlb_kms* km, unsigned sets)
+{
+    return for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        KmsGpu& kg = km->gpus[g];
+        for (int s = 0; s < km->n_sets; ++s) {
+            if (!((sets >> s) & 1u)) continue;
+            KmPrepArgs a{kg.craw + static_cast<size_t>(s) * km->d * km->k, km->data->shards[g].shift, km->d, km->k, km->DP, km->KP,
+                         kg.cfrag + static_cast<size_t>(s) * km->DP * km->KP, kg.cnorm + static_cast<size_t>(s) * km->KP, kg.cmax + s};
+            km_prepare_kernel<<<(km->KP + 127) / 128, 128, 0, gpu.stream>>>(a);
+            MLB_CUDA(cudaGetLastError());
+            km_cmax_kernel<<<1, 1, 0, gpu.stream>>>(a.cnorm, km->k, a.cmax);
+            MLB_CUDA(cudaGetLastError());
+            km->launches += 2;
+        }
+        return MLB_OK;
+    });
+}
+
+}  // namespace mlb
+
+extern "C" {
+
+int mlb_kms_supported(const mlb_data* data, int k, int n_sets)
+{
+    if (!data || k < 1 || n_sets < 1 || n_sets > kKmsMaxSets) return 0;
+    int DP = 0;
+    for (int cand : {4, 8, 16, 32, 64})
+        if (data->d <= cand) { DP = cand; break; }
+    if (!DP) return 0;   // wider points take the exact scan, one start at a time
+    const int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup;
+    constexpr size_t kSmemLimit = 227 * 1024;
+    const size_t stats = (KP == kKmGroup && DP <= 32) ? km_stats_small_smem_bytes(DP) : km_stats_smem_bytes(data->d, KP);
+    return km_sets_smem_bytes(DP, KP, 4, n_sets) + 1024 <= kSmemLimit && stats <= kSmemLimit;
+}
+
+int mlb_kms_create(mlb_ctx* ctx, mlb_data* data, int k, int n_sets, mlb_kms** out)
+{
+    MLB_ENTER(ctx);
+    MLB_REQUIRE(ctx && data && out, "mlb_kms_create: null argument");
+    MLB_REQUIRE(data->ctx == ctx, "mlb_kms_create: data belongs to another context");
+    MLB_REQUIRE(k >= 1, "mlb_kms_create: number of clusters must be positive");
+    MLB_REQUIRE(n_sets >= 1 && n_sets <= kKmsMaxSets, "mlb_kms_create: 1 to %d start sets per object (got %d)", kKmsMaxSets, n_sets);
+    MLB_REQUIRE(mlb_kms_supported(data, k, n_sets), "mlb_kms_create: %d sets of K=%d centroids at D=%d do not fit one CTA's shared memory (or D > 64): run the starts one at a time", n_sets, k, data->d);
+    const int d = data->d;
+    int DP = 0;
+    for (int cand : {4, 8, 16, 32, 64})
+        if (d <= cand) { DP = cand; break; }
+    const int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup;
+    constexpr size_t kSmemLimit = 227 * 1024;
+    // warps per CTA: the choice that keeps the most warps resident per SM, the narrowest CTA on ties (as km_warps_per_cta)
+    int nw = 4, best_warps = 0;
+    for (int cand : {4, 8, 16}) {
+        const size_t bytes = km_sets_smem_bytes(DP, KP, cand, n_sets) + 1024;
+        if (bytes > kSmemLimit) continue;
+        const int ctas = static_cast<int>(std::min<size_t>(kSmemLimit / bytes, 16 / cand));
+        if (ctas * cand > best_warps) { best_warps = ctas * cand; nw = cand; }
+    }
+    auto* km = new mlb_kms;
+    km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->n_sets = n_sets;
+    km->SV = n_sets * KP * (d + 1) + 8;
+    km->nw = nw;
+    km->fn = nw == 16 ? kms_kernel_for_nw<16>(DP) : nw == 8 ? kms_kernel_for_nw<8>(DP) : kms_kernel_for_nw<4>(DP);
+    km->smem = km_sets_smem_bytes(DP, KP, nw, n_sets);
+    km->stats_small = KP == kKmGroup && DP <= 32;
+    km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : km_stats_kernel_for<true>(DP);
+    km->smem_stats = km->stats_small ? km_stats_small_smem_bytes(DP) : km_stats_smem_bytes(d, KP);
+    km->gpus.resize(ctx->gpus.size());
+    const size_t S = static_cast<size_t>(n_sets);
+    int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        KmsGpu& kg = km->gpus[g];
+        const DataShard& sh = data->shards[g];
+        const size_t n = static_cast<size_t>(std::max<int64_t>(1, sh.n()));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.craw, sizeof(double) * S * d * k, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cold, sizeof(double) * S * d * k, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cfrag, sizeof(double) * S * DP * KP, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cnorm, sizeof(double) * S * KP, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.cmax, sizeof(double) * S, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.labels, sizeof(unsigned) * S * n, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.partials, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.vsum, sizeof(double) * kVirtualShards * km->SV, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.out, sizeof(double) * 4 * S, gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMallocFromPoolAsync(&kg.counter, sizeof(unsigned), gpu.pool, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(kg.labels, 0, sizeof(unsigned) * S * n, gpu.stream));   // labels_.resize(): zeros
+        MLB_CUDA(cudaMemsetAsync(kg.partials, 0, sizeof(double) * std::max<int64_t>(1, sh.n_chunks()) * km->SV, gpu.stream));   // frozen sets are never written
+        MLB_CUDA(cudaMemsetAsync(kg.vsum, 0, sizeof(double) * kVirtualShards * km->SV, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(kg.cold, 0, sizeof(double) * S * d * k, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(kg.cfrag, 0, sizeof(double) * S * DP * KP, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(kg.cnorm, 0, sizeof(double) * S * KP, gpu.stream));
+        MLB_CUDA(cudaMemsetAsync(kg.cmax, 0, sizeof(double) * S, gpu.stream));
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(km->smem)));
+        int per_sm = 0, sms = 0;
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn), nw * 32, km->smem));
+        MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
+        MLB_REQUIRE(per_sm >= 1, "mlb_kms_create: K-means kernel does not fit on an SM");
+        kg.grid = per_sm * sms;
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn_stats), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(km->smem_stats)));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn_stats), km->stats_small ? kKmThreads : kStThreads, km->smem_stats));
+        MLB_REQUIRE(per_sm >= 1, "mlb_kms_create: K-means statistics kernel does not fit on an SM");
+        kg.grid_stats = per_sm * sms;
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    });
+    if (rc != MLB_OK) { mlb_kms_destroy(km); return rc; }
+    *out = km;
+    return MLB_OK;
+}
+
+int mlb_kms_destroy(mlb_kms* km)
+{
+    MLB_ENTER(km ? km->ctx : nullptr);
+    if (!km) return MLB_OK;
+    for (size_t g = 0; g < km->gpus.size(); ++g) {
+        cudaSetDevice(km->ctx->gpus[g].device);
+        cudaStreamSynchronize(km->ctx->gpus[g].stream);
+        KmsGpu& kg = km->gpus[g];
+        for (void* ptr : {static_cast<void*>(kg.craw), static_cast<void*>(kg.cold), static_cast<void*>(kg.cfrag), static_cast<void*>(kg.cnorm),
+                          static_cast<void*>(kg.cmax), static_cast<void*>(kg.labels), static_cast<void*>(kg.partials), static_cast<void*>(kg.vsum),
+                          static_cast<void*>(kg.out), static_cast<void*>(kg.counter)})
+            if (ptr) cudaFreeAsync(ptr, km->ctx->gpus[g].stream);
+    }
+    km->reduce_scratch.release(km->ctx);
+    delete km;
+    return MLB_OK;
+}
+
+int mlb_kms_set_centroids(mlb_kms* km, int set, const double* centroids)
+{
+    MLB_ENTER(km ? km->ctx : nullptr);
+    MLB_REQUIRE(km && centroids, "mlb_kms_set_centroids: null argument");
+    MLB_REQUIRE(set >= 0 && set < km->n_sets, "mlb_kms_set_centroids: set %d out of range", set);
+    MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        MLB_CUDA(cudaMemcpyAsync(km->gpus[g].craw + static_cast<size_t>(set) * km->d * km->k, centroids, sizeof(double) * km->d * km->k, cudaMemcpyHostToDevice, gpu.stream));
+        MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+        return MLB_OK;
+    }));
+    MLB_TRY(kms_prepare(km, 1u << set));
+    km->have_centroids |= 1u << set;
+    km->have_stats &= ~(1u << set);
+    return MLB_OK;
+}
+
+int mlb_kms_get_centroids(mlb_kms* km, int set, double* centroids)
+{
+    MLB_ENTER(km ? km->ctx : nullptr);
+    MLB_REQUIRE(km && centroids, "mlb_kms_get_centroids: null argument");
+    MLB_REQUIRE(set >= 0 && set < km->n_sets, "mlb_kms_get_centroids: set %d out of range", set);
+    if (!((km->have_centroids >> set) & 1u)) { set_error("mlb_kms_get_centroids: centroids not set"); return MLB_ESTATE; }
+    Gpu& gpu = km->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    MLB_CUDA(cudaMemcpyAsync(centroids, km->gpus[0].craw + static_cast<size_t>(set) * km->d * km->k, sizeof(double) * km->d * km->k, cudaMemcpyDeviceToHost, gpu.stream));
+    MLB_CUDA(cudaStreamSynchronize(gpu.stream));
+    return MLB_OK;
+}
+
+int mlb_kms_assign(mlb_kms* km, unsigned int active, double* inertia, int64_t* n_changed)
+{
+    MLB_ENTER(km ? km->ctx : nullptr);
+    MLB_REQUIRE(km, "mlb_kms_assign: null argument");
+    MLB_REQUIRE(active != 0 && (active >> km->n_sets) == 0, "mlb_kms_assign: active mask 0x%x names no set or a set beyond %d", active, km->n_sets);
+    if ((km->have_centroids & active) != active) { set_error("mlb_kms_assign: centroids not set for an active set"); return MLB_ESTATE; }
+    mlb_ctx* ctx = km->ctx;
+    const int SD = km->d + 1;
+    MLB_TRY(for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
+        KmsGpu& kg = km->gpus[g];
+        const DataShard& sh = km->data->shards[g];
+        const int chunk = km->data->lay.chunk, n_chunks = static_cast<int>(sh.n_chunks());
+        if (n_chunks == 0) return MLB_OK;
+        KmArgs a{};
+        a.x = sh.x; a.n_local = sh.n(); a.d = km->d; a.k = km->k; a.KP = km->KP;
+        a.shift = sh.shift;
+        a.cfrag = kg.cfrag; a.cnorm = kg.cnorm; a.craw = kg.craw; a.cmax = kg.cmax;
+        a.labels = kg.labels; a.partials = kg.partials; a.pstride = km->SV;
+        a.chunk = chunk; a.n_chunks = n_chunks; a.counter = kg.counter;
+        a.n_sets = km->n_sets; a.active = active; a.label_stride = std::max<int64_t>(1, sh.n());
+        MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+        km->fn<<<std::min(kg.grid, n_chunks), km->nw * 32, km->smem, gpu.stream>>>(a);
+        MLB_CUDA(cudaGetLastError());
+        ++km->launches;
+        // statistics of the fresh labels: one launch per active set into that set's block of the partial vectors
+        for (int s = 0; s < km->n_sets; ++s) {
+            if (!((active >> s) & 1u)) continue;
+            KmArgs b{};
+            b.x = sh.x; b.n_local = sh.n(); b.d = km->d; b.k = km->k; b.KP = km->KP;
+            b.shift = sh.shift; b.labels = kg.labels + static_cast<size_t>(s) * a.label_stride; b.partials = kg.partials; b.pstride = km->SV;
+            b.chunk = chunk; b.n_chunks = n_chunks; b.counter = kg.counter;
+            b.k_lo = 0; b.stat_off = s * km->KP * SD;
+            MLB_CUDA(cudaMemsetAsync(kg.counter, 0, sizeof(unsigned), gpu.stream));
+            km->fn_stats<<<std::min(kg.grid_stats, n_chunks), km->stats_small ? kKmThreads : kStThreads, km->smem_stats, gpu.stream>>>(b);
+            MLB_CUDA(cudaGetLastError());
+            ++km->launches;
+        }
+        return MLB_OK;
+    }));
+    std::vector<double*> partials, vsum;
+    for (KmsGpu& kg : km->gpus) { partials.push_back(kg.partials); vsum.push_back(kg.vsum); }
+    MLB_TRY(reduce_and_exchange(km->data, partials, vsum, km->SV, km->reduce_scratch));
+    km->launches += static_cast<int64_t>(ctx->gpus.size());
+    double host[4 * kKmsMaxSets] = {};
+    {
+        Gpu& gpu = ctx->gpus[0];
+        MLB_CUDA(cudaSetDevice(gpu.device));
+        kms_scalars_kernel<<<1, 32, 0, gpu.stream>>>(km->gpus[0].vsum, km->SV, km->n_sets * km->KP * SD, km->n_sets, km->gpus[0].out);
+        MLB_CUDA(cudaGetLastError());
+        ++km->launches;
+        MLB_CUDA(cudaMemcpyAsync(host, km->gpus[0].out, sizeof(double) * 4 * km->n_sets, cudaMemcpyDeviceToHost, gpu.stream));
+    }
+    MLB_TRY(mlb_ctx_synchronize(ctx));
+    for (int s = 0; s < km->n_sets; ++s) {
+        if (!((active >> s) & 1u)) continue;
+        if (inertia) inertia[s] = host[4 * s + 1];
+        if (n_changed) n_changed[s] = static_cast<int64_t>(host[4 * s + 2]);
+    }
+    km->have_stats |= active;
+    return MLB_OK;
+}
+
+int mlb_kms_update(mlb_kms* km, unsigned int active, double* centroid_shift_sq)
+{
+    MLB_ENTER(km ? km->ctx : nullptr);
+    MLB_REQUIRE(km, "mlb_kms_update: null argument");
+    MLB_REQUIRE(active != 0 && (active >> km->n_sets) == 0, "mlb_kms_update: active mask 0x%x names no set or a set beyond %d", active, km->n_sets);
+    if ((km->have_stats & active) != active) { set_error("mlb_kms_update: no assignment to update an active set from"); return MLB_ESTATE; }
+    const int SD = km->d + 1;
+    MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        KmsGpu& kg = km->gpus[g];
+        for (int s = 0; s < km->n_sets; ++s) {
+            if (!((active >> s) & 1u)) continue;
+            const size_t c_off = static_cast<size_t>(s) * km->d * km->k;
+            KmUpdateArgs a{kg.vsum + static_cast<size_t>(s) * km->KP * SD, km->data->shards[g].shift, km->d, km->k, km->KP, km->SV, kg.craw + c_off, kg.cold + c_off, kg.out + 4 * s};
+            km_update_kernel<<<1, 256, 0, gpu.stream>>>(a);
+            MLB_CUDA(cudaGetLastError());
+            ++km->launches;
+        }
+        return MLB_OK;
+    }));
+    MLB_TRY(kms_prepare(km, active));
+    double host[4 * kKmsMaxSets] = {};
+    Gpu& gpu = km->ctx->gpus[0];
+    MLB_CUDA(cudaSetDevice(gpu.device));
+    MLB_CUDA(cudaMemcpyAsync(host, km->gpus[0].out, sizeof(double) * 4 * km->n_sets, cudaMemcpyDeviceToHost, gpu.stream));
+    MLB_TRY(mlb_ctx_synchronize(km->ctx));
+    for (int s = 0; s < km->n_sets; ++s)
+        if (((active >> s) & 1u) && centroid_shift_sq) centroid_shift_sq[s] = host[4 * s];
+    km->have_stats &= ~active;
+    return MLB_OK;
+}
+
+int mlb_kms_get_labels(mlb_kms* km, int set, unsigned int* labels)
+{
+    MLB_ENTER(km ? km->ctx : nullptr);
+    MLB_REQUIRE(km && labels, "mlb_kms_get_labels: null argument");
+    MLB_REQUIRE(set >= 0 && set < km->n_sets, "mlb_kms_get_labels: set %d out of range", set);
+    const int64_t host_begin = km->ctx->rank_mode ? km->data->shards[0].begin : 0;
+    MLB_TRY(for_each_gpu(km->ctx, [&](int g, Gpu& gpu) -> int {
+        const DataShard& sh = km->data->shards[g];
+        const size_t stride = static_cast<size_t>(std::max<int64_t>(1, sh.n()));
+        if (sh.n() > 0) MLB_TRY(staged_d2h(gpu, labels + (sh.begin - host_begin), km->gpus[g].labels + static_cast<size_t>(set) * stride, sizeof(unsigned) * sh.n()));
+        return MLB_OK;
+    }));
+    return mlb_ctx_synchronize(km->ctx);
+}
+
+int mlb_kms_launch_count(const mlb_kms* km, int64_t* launches)
+{
+    MLB_REQUIRE(km && launches, "mlb_kms_launch_count: null argument");
     *launches = km->launches;
     return MLB_OK;
 }

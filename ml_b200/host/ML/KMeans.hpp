@@ -87,6 +87,10 @@ namespace ml
             mutable std::unique_ptr<detail::KmDevice> device_; /**< HBM-resident state of the last fit */
 
             bool fit_once(DataView data, detail::KmDevice& device);
+            /** Draws the initial centroids of one start (KMeans.cpp:77). */
+            void draw_initial_centroids(DataView data, detail::KmDevice& device);
+            /** The starts of a multi-start fit in lockstep groups of up to four (same results as one after the other). */
+            bool fit_lockstep(DataView data, detail::KmDevice& device);
         };
     }
 }

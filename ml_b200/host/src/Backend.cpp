@@ -272,6 +272,54 @@ namespace ml
 			labels.resize(static_cast<size_t>(data_->cols()));
 			check(mlb_km_get_labels(km_, labels.data()), "KMeans labels");
 		}
+
+		bool KmSetsDevice::supported(const DeviceData& data, unsigned int number_clusters, unsigned int number_sets)
+		{
+			return mlb_kms_supported(data.handle(), static_cast<int>(number_clusters), static_cast<int>(number_sets)) != 0;
+		}
+
+		KmSetsDevice::KmSetsDevice(std::shared_ptr<DeviceData> data, unsigned int number_clusters, unsigned int number_sets)
+			: data_(std::move(data)), number_sets_(number_sets)
+		{
+			check(mlb_kms_create(shared_context(), data_->handle(), static_cast<int>(number_clusters), static_cast<int>(number_sets), &kms_), "KMeans start sets");
+		}
+
+		KmSetsDevice::~KmSetsDevice()
+		{
+			mlb_kms_destroy(kms_);
+		}
+
+		void KmSetsDevice::set_centroids(unsigned int set, const Eigen::MatrixXd& centroids)
+		{
+			check(mlb_kms_set_centroids(kms_, static_cast<int>(set), centroids.data()), "KMeans centroids");
+		}
+
+		void KmSetsDevice::get_centroids(unsigned int set, Eigen::MatrixXd& centroids)
+		{
+			check(mlb_kms_get_centroids(kms_, static_cast<int>(set), centroids.data()), "KMeans centroids");
+		}
+
+		void KmSetsDevice::assign(unsigned int active, double* inertia, std::int64_t* changed)
+		{
+			int64_t n_changed[4] = {0, 0, 0, 0};
+			check(mlb_kms_assign(kms_, active, inertia, n_changed), "KMeans assignment step");
+			for (unsigned int s = 0; s < number_sets_; ++s) {
+				if ((active >> s) & 1u) {
+					changed[s] = n_changed[s];
+				}
+			}
+		}
+
+		void KmSetsDevice::update(unsigned int active, double* shift)
+		{
+			check(mlb_kms_update(kms_, active, shift), "KMeans update step");
+		}
+
+		void KmSetsDevice::get_labels(unsigned int set, std::vector<unsigned int>& labels)
+		{
+			labels.resize(static_cast<size_t>(data_->cols()));
+			check(mlb_kms_get_labels(kms_, static_cast<int>(set), labels.data()), "KMeans labels");
+		}
 	}
 }
 

@@ -108,5 +108,30 @@ namespace ml
 			std::shared_ptr<DeviceData> data_;
 			mlb_km* km_ = nullptr;
 		};
+
+		/** Up to four starts of a multi-start K-means fit advanced in lockstep on one resident copy of the points
+		(mlb_kms, KMeans.cpp:29-47): one pass of the assignment kernel scores every point against all active starts. */
+		class KmSetsDevice
+		{
+		public:
+			/** Whether `number_sets` starts of `number_clusters` centroids can share a pass on these points. */
+			static bool supported(const DeviceData& data, unsigned int number_clusters, unsigned int number_sets);
+			KmSetsDevice(std::shared_ptr<DeviceData> data, unsigned int number_clusters, unsigned int number_sets);
+			~KmSetsDevice();
+			KmSetsDevice(const KmSetsDevice&) = delete;
+			KmSetsDevice& operator=(const KmSetsDevice&) = delete;
+			unsigned int number_sets() const { return number_sets_; }
+			void set_centroids(unsigned int set, const Eigen::MatrixXd& centroids);
+			void get_centroids(unsigned int set, Eigen::MatrixXd& centroids);
+			/** Assignment step of every start in `active` (bit s = start s): inertia[s], changed[s] for those starts. */
+			void assign(unsigned int active, double* inertia, std::int64_t* changed);
+			/** Update step of every start in `active`: squared centroid shift per start. */
+			void update(unsigned int active, double* shift);
+			void get_labels(unsigned int set, std::vector<unsigned int>& labels);
+		private:
+			std::shared_ptr<DeviceData> data_;
+			mlb_kms* kms_ = nullptr;
+			unsigned int number_sets_ = 0;
+		};
 	}
 }

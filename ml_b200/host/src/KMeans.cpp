@@ -85,6 +85,9 @@ namespace ml
 			detail::KmDevice& device = *device_;
 			if (number_initialisations_ == 1) {
 				fit_once(data, device);
+			} else if (!verbose_ && detail::KmSetsDevice::supported(*device.data(), number_clusters_, 2)) {
+				// Best of number_initialisations_ runs by inertia (KMeans.cpp:29-47), the runs advanced in lockstep.
+				return fit_lockstep(data, device);
 			} else {
 				// Best of number_initialisations_ runs by inertia (KMeans.cpp:29-47).
 				double min_inertia = std::numeric_limits<double>::infinity();
@@ -111,9 +114,8 @@ namespace ml
 			return converged_;
 		}
 
-		bool KMeans::fit_once(DataView data, detail::KmDevice& device)
+		void KMeans::draw_initial_centroids(DataView data, detail::KmDevice& device)
 		{
-			converged_ = false;
 			const CentroidsInitialiser& initialiser = *centroids_initialiser_;
 			if (typeid(initialiser) == typeid(KPP)) {
 				// the built-in K-means++: distance passes on the device, draws here (Clustering.cpp:39-59)
@@ -121,6 +123,113 @@ namespace ml
 			} else {
 				initialiser.init(data, prng_, number_clusters_, centroids_);
 			}
+		}
+
+		bool KMeans::fit_lockstep(DataView data, detail::KmDevice& device)
+		{
+			// The reference runs fit_once number_initialisations_ times in a row (KMeans.cpp:34-42).  Only the initialiser
+			// consumes the PRNG (KMeans.cpp:77), so the starts' initial centroids are drawn first, in the order the reference
+			// draws them; after that the starts are independent Lloyd loops over the same points and are advanced together,
+			// four to a pass over the data.  Every start keeps its own step counter and stopping tests (KMeans.cpp:80-109).
+			const unsigned int total = number_initialisations_;
+			std::vector<Eigen::MatrixXd> start_centroids(total);
+			for (unsigned int i = 0; i < total; ++i) {
+				draw_initial_centroids(data, device);
+				start_centroids[i] = centroids_;
+			}
+			double min_inertia = std::numeric_limits<double>::infinity();
+			Eigen::MatrixXd best_centroids;
+			bool any_converged = false;
+			for (unsigned int first = 0, count = 0; first < total; first += count) {
+				count = std::min(4u, total - first);
+				while (count > 1 && !detail::KmSetsDevice::supported(*device.data(), number_clusters_, count)) {
+					--count;   // fewer starts per pass when four centroid images do not fit the shared memory
+				}
+				detail::KmSetsDevice sets(device.data(), number_clusters_, count);
+				bool converged[4] = {false, false, false, false};
+				double inertia[4] = {0, 0, 0, 0};
+				unsigned int iterations[4] = {0, 0, 0, 0};
+				for (unsigned int s = 0; s < count; ++s) {
+					sets.set_centroids(s, start_centroids[first + s]);
+				}
+				unsigned int active = (1u << count) - 1u;
+				for (unsigned int step = 0; step < maximum_steps_ && active; ++step) {
+					std::int64_t changed[4] = {0, 0, 0, 0};
+					sets.assign(active, inertia, changed);
+					for (unsigned int s = 0; s < count; ++s) {
+						if (!((active >> s) & 1u)) {
+							continue;
+						}
+						iterations[s] = step + 1;
+						if (step > 0 && changed[s] == 0) {
+							// old_labels_ == labels_ (KMeans.cpp:84-89): the centroids are not updated again
+							converged[s] = true;
+							active &= ~(1u << s);
+						}
+					}
+					if (!active) {
+						break;
+					}
+					double shift[4] = {0, 0, 0, 0};
+					sets.update(active, shift);
+					if (step > 0) {
+						unsigned int reassign = 0;
+						for (unsigned int s = 0; s < count; ++s) {
+							if (((active >> s) & 1u) && shift[s] < absolute_tolerance_) {
+								reassign |= 1u << s;
+							}
+						}
+						if (reassign) {
+							// the closing assignment_step of KMeans.cpp:104-106
+							sets.assign(reassign, inertia, changed);
+							for (unsigned int s = 0; s < count; ++s) {
+								if ((reassign >> s) & 1u) {
+									converged[s] = true;
+								}
+							}
+							active &= ~reassign;
+						}
+					}
+				}
+				// in the order of the reference's loop over the starts (KMeans.cpp:34-42)
+				for (unsigned int s = 0; s < count; ++s) {
+					if (converged[s]) {
+						if (inertia[s] < min_inertia) {
+							min_inertia = inertia[s];
+							best_centroids.resize(centroids_.rows(), centroids_.cols());
+							sets.get_centroids(s, best_centroids);
+						}
+						any_converged = true;
+					}
+				}
+				if (first + count >= total) {
+					// what the last fit_once leaves behind: its centroids, inertia, labels and step count
+					const unsigned int s = count - 1;
+					sets.get_centroids(s, centroids_);
+					inertia_ = inertia[s];
+					number_iterations_ = iterations[s];
+					if (!any_converged) {
+						sets.get_labels(s, labels_);
+					}
+				}
+			}
+			converged_ = any_converged;
+			if (converged_) {
+				centroids_ = best_centroids;
+				device.set_centroids(centroids_);
+				std::int64_t changed = 0;
+				inertia_ = device.assign(changed);
+				labels_on_host_ = false;   // downloaded on first access to labels()
+			} else {
+				labels_on_host_ = true;    // no start converged: the last start's labels, already here
+			}
+			return converged_;
+		}
+
+		bool KMeans::fit_once(DataView data, detail::KmDevice& device)
+		{
+			converged_ = false;
+			draw_initial_centroids(data, device);
 			device.set_centroids(centroids_);
 			for (unsigned int step = 0; step < maximum_steps_; ++step) {
 				std::int64_t changed = 0;
