@@ -193,14 +193,23 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
                 }
             } else {
                 // ---------------- log-sum-exp over the 4 lanes that share a point
+                double mxs[2], sums[2];
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
-                    const int pl = mt * 8 + g;
+#ifdef MLB_EM_FMAX_SHIFT
                     double mx = -INFINITY;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) mx = fmax(mx, fmax(acc[mt][nt][0], acc[mt][nt][1]));
                     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
                     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+#else
+                    int mkey = lse_key(acc[mt][0][0]);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) mkey = max(mkey, max(lse_key(acc[mt][nt][0]), lse_key(acc[mt][nt][1])));
+                    mkey = max(mkey, __shfl_xor_sync(0xffffffffu, mkey, 1));
+                    mkey = max(mkey, __shfl_xor_sync(0xffffffffu, mkey, 2));
+                    const double mx = lse_shift_of_key(mkey);   // within 2^-20 of the largest term (fastmath.cuh)
+#endif
                     double sum = 0.0;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
@@ -210,10 +219,20 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
                     }
                     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-                    const double inv = reciprocal_of_sum(sum);
+                    mxs[mt] = mx;
+                    sums[mt] = sum;
+                }
+                // One reciprocal per lane instead of two: the four lanes of a quad hold the same two sums, so the even lanes
+                // invert the first point's and the odd lanes the second point's, and a shuffle hands both to everybody.
+                const double inv_mine = reciprocal_of_sum((c & 1) ? sums[1] : sums[0]);
+                const double invs[2] = {__shfl_sync(0xffffffffu, inv_mine, lane & ~1), __shfl_sync(0xffffffffu, inv_mine, lane | 1)};
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int pl = mt * 8 + g;
+                    const double inv = invs[mt];
                     if (c == 0 && pl < nvalid) {
-                        ll_acc += mx;
-                        ll_prod *= sum;
+                        ll_acc += mxs[mt];
+                        ll_prod *= sums[mt];
                     }
                     if (MODE == 0) {
 #pragma unroll

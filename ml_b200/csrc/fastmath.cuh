@@ -120,6 +120,22 @@ __device__ __forceinline__ double exp_nonpositive(double x, const double* table 
     return tiny ? 0.0 : scaled;
 }
 
+// Shift of a log-sum-exp without FP64 comparisons.  The shift only has to be CLOSE to the largest term (log sum_k e^(a_k) =
+// m + log sum_k e^(a_k - m) for any m), so the maximum is taken over 32-bit keys on the integer pipe: the high word of a
+// double, with the low 31 bits flipped for negative values, orders like the value (to 20 mantissa bits).  fmax on doubles is
+// DSETP + selects on the FP64 pipe, which the EM kernels share with their DMMAs: 6 per point and quad in the fused kernels.
+// The shift handed back is the key's double with a zero low word: >= every negative term, and below a positive maximum by
+// at most 2^-20 of it, so the largest argument of the exponential is <= 1e-6 |m| (exp_nonpositive is exact there too).
+__device__ __forceinline__ int lse_key(double v)
+{
+    const int hi = __double2hiint(v);
+    return hi ^ ((hi >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ double lse_shift_of_key(int key)
+{
+    return __hiloint2double(key ^ ((key >> 31) & 0x7fffffff), 0);
+}
+
 // 1 / s for s in [1, 2^30] (a sum of exponentials whose largest term is 1): the hardware's reciprocal seed and two
 // Newton steps, 4 FMAs, within 1 ulp; no special cases to test for, unlike the general division.
 __device__ __forceinline__ double reciprocal_of_sum(double s)

@@ -596,6 +596,211 @@ __global__ void __launch_bounds__(kStThreads) km_stats_kernel(const KmArgs p)
     }
 }
 
+// ---------------------------------------------------------------- update statistics by counting sort (r02)
+// The owner-warp kernel above spends ~43 warp instructions per point (ncu r02h at C5: 1.51 ms per 12.5M points, 30 % of the
+// DRAM throughput, every warp scanning every label and read-modify-writing shared memory once per owned point).  Here a
+// CTA takes a whole chunk (<= 4096 points) at a time:
+//   1. stable counting sort of the chunk's point indices by label: every warp ranks its own contiguous 1/8 of the chunk
+//      with __match_any_sync (32 points per step) into a per-warp count table, a thread per cluster turns the 8 counts into
+//      bases, one warp scans the cluster totals, every point's slot is start[label] + base[warp][label] + rank;
+//   2. the clusters are dealt to the 8 warps in contiguous runs of about chunk/8 points; a warp walks its clusters'
+//      points in index order, lane = coordinate, gathering the rows straight from global memory (a row is D contiguous
+//      doubles: full sectors, every row of the chunk is read exactly once) into a register sum that goes out to the
+//      chunk's partial vector with one coalesced store.  No shared-memory statistics at all (10 KB instead of 99 KB per CTA:
+//      the SM fills up with warps, which is what the gathers need), no read-modify-write per point.
+// Per cluster and chunk the sum is sequential in index order, exactly as before; the partial vectors therefore hold the
+// same values as the owner-warp kernel's (which added the same terms in the same order into shared memory).
+constexpr int kSsThreads = 256;
+constexpr int kSsMaxChunk = 4096;
+static_assert(kSsThreads == kStThreads, "the launch sites use one block size for both statistics kernels");
+
+constexpr int kSsRows = 8;         // rows per gather group (two groups in flight per warp)
+
+inline size_t km_stats_sorted_smem_bytes(int DP, int KP, int chunk)
+{
+    const size_t dps = static_cast<size_t>(DP < 32 ? 32 : DP);
+    return sizeof(double) * (8 * 2 * kSsRows * dps) + sizeof(unsigned short) * (8 * static_cast<size_t>(KP) + 3 * static_cast<size_t>(chunk))
+           + sizeof(int) * (static_cast<size_t>(KP) + 1 + 8);
+}
+
+template <int DP, bool BLOCKED>
+__global__ void __launch_bounds__(kSsThreads) km_stats_sorted_kernel(const KmArgs p)
+{
+    constexpr int NJ = (DP + 31) / 32;   // coordinates per lane
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int KP = p.KP, d = p.d, SD = d + 1, T = p.chunk;
+    constexpr int DPS = DP < 32 ? 32 : DP;                                          // doubles per staged row
+    double* stage = reinterpret_cast<double*>(smraw) + (threadIdx.x >> 5) * (2 * kSsRows * DPS);   // [8 warps][2][kSsRows][DPS] gathered rows
+    int* start = reinterpret_cast<int*>(reinterpret_cast<double*>(smraw) + 8 * 2 * kSsRows * DPS);   // [KP + 1] first slot of every cluster in `sorted`
+    unsigned short* cnt = reinterpret_cast<unsigned short*>(start + KP + 1 + 8);   // [8][KP] per-warp counts, then exclusive bases
+    unsigned short* labs = cnt + 8 * KP;                                            // [T] label of every point (0xffff: not in this block)
+    unsigned short* rank = labs + T;                                                // [T] rank among the warp's points of the same label
+    unsigned short* sorted = rank + T;                                              // [T] point indices ordered by (label, index)
+    __shared__ int s_next;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_warp = T / 8;   // T is a multiple of 128
+    double shv[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) shv[j] = lane + 32 * j < d ? p.shift[lane + 32 * j] : 0.0;
+
+    for (;;) {
+        __syncthreads();   // the previous chunk's tables have been read
+        if (tid == 0) s_next = static_cast<int>(atomicAdd(p.counter, 1u));
+        for (int i = tid; i < 4 * KP; i += kSsThreads) reinterpret_cast<unsigned*>(cnt)[i] = 0u;
+        __syncthreads();
+        const int chunk = s_next;
+        if (chunk >= p.n_chunks) break;
+        const long long p_begin = static_cast<long long>(chunk) * p.chunk;
+        const int nvalid = static_cast<int>(p_begin + p.chunk < p.n_local ? p.chunk : p.n_local - p_begin);
+
+        // ---- 1a. every warp ranks its own points, 32 at a time in index order
+        unsigned short* cw = cnt + warp * KP;
+        const int w_end = (warp + 1) * per_warp;   // per_warp is a multiple of 16, not always of 32
+        for (int i0 = warp * per_warp; i0 < w_end; i0 += 32) {
+            const int i = i0 + lane;
+            int lab = -1;
+            if (i < w_end && i < nvalid) {
+                lab = static_cast<int>(p.labels[p_begin + i]) - (BLOCKED ? p.k_lo : 0);
+                if (lab < 0 || lab >= KP) lab = -1;
+            }
+            const unsigned same = __match_any_sync(0xffffffffu, lab >= 0 ? lab : -1 - lane);
+            const int before = __popc(same & ((1u << lane) - 1u));
+            const int base = lab >= 0 ? cw[lab] : 0;
+            __syncwarp();
+            if (lab >= 0 && before == 0) cw[lab] = static_cast<unsigned short>(base + __popc(same));
+            __syncwarp();
+            if (i < w_end) {
+                labs[i] = lab >= 0 ? static_cast<unsigned short>(lab) : 0xffffu;
+                rank[i] = static_cast<unsigned short>(base + before);
+            }
+        }
+        __syncthreads();
+        // ---- 1b. per cluster: the warps' counts become exclusive bases, the total goes to start[]
+        for (int kk = tid; kk < KP; kk += kSsThreads) {
+            int run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const int c = cnt[w * KP + kk];
+                cnt[w * KP + kk] = static_cast<unsigned short>(run);
+                run += c;
+            }
+            start[kk] = run;
+        }
+        __syncthreads();
+        // ---- 1c. exclusive scan of the totals (warp 0; KP is a multiple of 32)
+        if (warp == 0) {
+            const int per = KP / 32;
+            int local = 0;
+            for (int j = 0; j < per; ++j) local += start[lane * per + j];
+            int incl = local;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            int run = incl - local;
+            for (int j = 0; j < per; ++j) {
+                const int c = start[lane * per + j];
+                start[lane * per + j] = run;
+                run += c;
+            }
+            if (lane == 31) start[KP] = run;
+        }
+        __syncthreads();
+        // ---- 1d. placement
+        for (int i = tid; i < T; i += kSsThreads) {
+            const unsigned lab = labs[i];
+            if (lab != 0xffffu) sorted[start[lab] + cnt[(i / per_warp) * KP + lab] + rank[i]] = static_cast<unsigned short>(i);
+        }
+        __syncthreads();
+        // ---- 2. clusters in contiguous runs of about total / 8 points per warp: first cluster whose start is >= the share
+        const int total = start[KP];
+        auto first_cluster = [&](int w) {
+            if (w >= 8) return KP;
+            const int target = static_cast<int>((static_cast<long long>(total) * w) / 8);
+            int lo = 0, hi = KP;   // first kk in [0, KP] with start[kk] >= target, but never beyond a cluster with points
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (start[mid] >= target) hi = mid; else lo = mid + 1;
+            }
+            return w == 0 ? 0 : lo;
+        };
+        const int c_lo = first_cluster(warp), c_hi = first_cluster(warp + 1);
+        double* out = BLOCKED ? p.partials + static_cast<long long>(chunk) * p.pstride + static_cast<long long>(p.k_lo) * SD + p.stat_off
+                              : p.partials + static_cast<long long>(chunk) * km_sv(d, KP);
+        const double* xg = p.x + p_begin * d;
+        // The warp walks the sorted points of its clusters 32 at a time: every lane fetches one entry's row offset and
+        // label and whether it is the LAST row of its cluster; the rows are gathered 8 at a time with cp.async into the warp's
+        // two staging buffers (16 rows in flight per warp: the pass is bound by memory-level parallelism, 3.25 GB of rows at
+        // C5; plain loads were sunk next to their uses by ptxas, one row in flight) and added in order; after a cluster's
+        // last row the sum goes out with a predicated store and the accumulator restarts.
+        constexpr int NB = kSsRows;
+        double acc[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[j] = 0.0;
+        const int s_w = start[c_lo], e_w = start[c_hi];
+        for (int jb = s_w; jb < e_w; jb += 32) {
+            const int pos = jb + lane;
+            const bool ok = pos < e_w;
+            const int pt = ok ? sorted[pos] : 0;
+            const int lab = ok ? labs[pt] : -1;
+            int next_lab = __shfl_down_sync(0xffffffffu, lab, 1);
+            if (lane == 31) next_lab = pos + 1 < e_w ? labs[sorted[pos + 1]] : -1;
+            const unsigned last_mask = __ballot_sync(0xffffffffu, ok && lab != next_lab);
+            const int off = pt * d;                    // < 4096 * 128
+            const int row_out = lab * SD;              // where this entry's cluster goes in the partial vector
+            const int n = e_w - jb < 32 ? e_w - jb : 32;
+            // rows of group h / NB -> the warp's staging buffer (h / NB) & 1, asynchronously: every lane copies the
+            // coordinates it will add itself, so a lane only ever waits for its own copies
+            auto gather = [&](int h) {
+                double* dst = stage + ((h / NB) & 1) * (NB * DPS);
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    const int o = __shfl_sync(0xffffffffu, off, h + u);
+                    if (h + u < n) {
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j)
+                            if (lane + 32 * j < d) km_cp_async8(dst + u * DPS + lane + 32 * j, xg + o + lane + 32 * j);
+                    }
+                }
+                km_cp_async_commit();
+            };
+            gather(0);
+#pragma unroll 1
+            for (int h = 0; h < n; h += NB) {
+                if (h + NB < n) {
+                    gather(h + NB);
+                    km_cp_async_wait<1>();
+                } else {
+                    km_cp_async_wait<0>();
+                }
+                __syncwarp();   // also keeps the compiler from reading the buffer above the wait
+                const double* src = stage + ((h / NB) & 1) * (NB * DPS);
+#pragma unroll
+                for (int u = 0; u < NB; ++u) {
+                    const int ro = __shfl_sync(0xffffffffu, row_out, h + u);
+                    const bool flush = (last_mask >> (h + u)) & 1u;
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        const double v = (h + u < n && lane + 32 * j < d) ? src[u * DPS + lane + 32 * j] : shv[j];   // shv: adds zero
+                        acc[j] += v - shv[j];
+                        if (flush && lane + 32 * j < d) out[ro + lane + 32 * j] = acc[j];
+                        acc[j] = flush ? 0.0 : acc[j];
+                    }
+                }
+            }
+        }
+        // counts, and zeros for the clusters without points in this chunk: a lane per cluster
+        for (int kk = c_lo + lane; kk < c_hi; kk += 32) {
+            const int count = start[kk + 1] - start[kk];
+            double* row = out + static_cast<long long>(kk) * SD;
+            row[d] = static_cast<double>(count);
+            if (count == 0)
+                for (int dim = 0; dim < d; ++dim) row[dim] = 0.0;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- update statistics, K <= 32
 // With few clusters the owner-warp scheme above leaves most warps idle (K = 3: one warp does everything).  Here the
 // statistics are a tensor-pipe product instead: S[k][col] = sum_i onehot(label_i == k) * [z_i, 1][col], a
@@ -879,6 +1084,28 @@ static KmKernelFn km_stats_small_kernel_for(int DP)
 }
 
 template <bool BLOCKED>
+static KmKernelFn km_stats_sorted_kernel_for(int DP)
+{
+    switch (DP) {
+    case 4: return km_stats_sorted_kernel<4, BLOCKED>;
+    case 8: return km_stats_sorted_kernel<8, BLOCKED>;
+    case 16: return km_stats_sorted_kernel<16, BLOCKED>;
+    case 32: return km_stats_sorted_kernel<32, BLOCKED>;
+    case 64: return km_stats_sorted_kernel<64, BLOCKED>;
+    case 128: return km_stats_sorted_kernel<128, BLOCKED>;
+    default: return nullptr;
+    }
+}
+
+// MLB200_KM_STATS=owner: developer override, the owner-warp statistics kernel instead of the counting-sort one (same values).
+static bool km_stats_use_sorted(int chunk, int KP)
+{
+    if (const char* env = std::getenv("MLB200_KM_STATS"))
+        if (std::strcmp(env, "owner") == 0) return false;
+    return chunk <= kSsMaxChunk && KP < 0xffff;
+}
+
+template <bool BLOCKED>
 static KmKernelFn km_stats_kernel_for(int DP)
 {
     switch (DP) {
@@ -1053,6 +1280,10 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
     km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : nblocks == 1 ? km_stats_kernel_for<false>(DP) : km_stats_kernel_for<true>(DP);
     km->smem = smem;
     km->smem_stats = smem_stats;
+    if (!km->stats_small && km_stats_use_sorted(data->lay.chunk, KB)) {
+        km->fn_stats = nblocks == 1 ? km_stats_sorted_kernel_for<false>(DP) : km_stats_sorted_kernel_for<true>(DP);
+        km->smem_stats = km_stats_sorted_smem_bytes(DP, KB, data->lay.chunk);
+    }
     km->gpus.resize(ctx->gpus.size());
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {
         KmGpu& kg = km->gpus[g];
@@ -1086,8 +1317,8 @@ int mlb_km_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_km** out)
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means kernel does not fit on an SM");
         kg.grid = per_sm * sms;
-        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn_stats), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_stats)));
-        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn_stats), km->stats_small ? kKmThreads : kStThreads, smem_stats));
+        MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(km->fn_stats), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(km->smem_stats)));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(km->fn_stats), km->stats_small ? kKmThreads : kStThreads, km->smem_stats));
         MLB_REQUIRE(per_sm >= 1, "mlb_km_create: K-means statistics kernel does not fit on an SM");
         kg.grid_stats = per_sm * sms;
         MLB_CUDA(cudaStreamSynchronize(gpu.stream));
@@ -1420,13 +1651,19 @@ int mlb_kms_create(mlb_ctx* ctx, mlb_data* data, int k, int n_sets, mlb_kms** ou
         if (d <= cand) { DP = cand; break; }
     const int KP = (k + kKmGroup - 1) / kKmGroup * kKmGroup;
     constexpr size_t kSmemLimit = 227 * 1024;
-    // warps per CTA: the choice that keeps the most warps resident per SM, the narrowest CTA on ties (as km_warps_per_cta)
-    int nw = 4, best_warps = 0;
-    for (int cand : {4, 8, 16}) {
-        const size_t bytes = km_sets_smem_bytes(DP, KP, cand, n_sets) + 1024;
-        if (bytes > kSmemLimit) continue;
-        const int ctas = static_cast<int>(std::min<size_t>(kSmemLimit / bytes, 16 / cand));
-        if (ctas * cand > best_warps) { best_warps = ctas * cand; nw = cand; }
+    // Warps per CTA: the one-start kernel's choice for this shape whenever the sets' images leave room for it (a chunk's
+    // inertia partial is summed per warp, so with the same number of warps it is bit for bit the one-start value; labels,
+    // changed counts and statistics do not depend on it), else the choice that keeps the most warps resident per SM.
+    int nw = km_warps_per_cta(DP, KP);
+    if (km_sets_smem_bytes(DP, KP, nw, n_sets) + 1024 > kSmemLimit) {
+        int best_warps = 0;
+        nw = 4;
+        for (int cand : {4, 8, 16}) {
+            const size_t bytes = km_sets_smem_bytes(DP, KP, cand, n_sets) + 1024;
+            if (bytes > kSmemLimit) continue;
+            const int ctas = static_cast<int>(std::min<size_t>(kSmemLimit / bytes, 16 / cand));
+            if (ctas * cand > best_warps) { best_warps = ctas * cand; nw = cand; }
+        }
     }
     auto* km = new mlb_kms;
     km->ctx = ctx; km->data = data; km->d = d; km->k = k; km->DP = DP; km->KP = KP; km->n_sets = n_sets;
@@ -1437,6 +1674,10 @@ int mlb_kms_create(mlb_ctx* ctx, mlb_data* data, int k, int n_sets, mlb_kms** ou
     km->stats_small = KP == kKmGroup && DP <= 32;
     km->fn_stats = km->stats_small ? km_stats_small_kernel_for(DP) : km_stats_kernel_for<true>(DP);
     km->smem_stats = km->stats_small ? km_stats_small_smem_bytes(DP) : km_stats_smem_bytes(d, KP);
+    if (!km->stats_small && km_stats_use_sorted(data->lay.chunk, KP)) {
+        km->fn_stats = km_stats_sorted_kernel_for<true>(DP);
+        km->smem_stats = km_stats_sorted_smem_bytes(DP, KP, data->lay.chunk);
+    }
     km->gpus.resize(ctx->gpus.size());
     const size_t S = static_cast<size_t>(n_sets);
     int rc = for_each_gpu(ctx, [&](int g, Gpu& gpu) -> int {

@@ -4,6 +4,7 @@
 #include "ML/KMeans.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <iostream>
 #include <limits>
 #include <stdexcept>
@@ -15,6 +16,17 @@ namespace ml
 {
 	namespace Clustering
 	{
+		namespace
+		{
+			/** MLPP_KMEANS_LOCKSTEP=0: developer switch, the starts of a multi-start fit one after the other (same results;
+			tools/bm_kmeans.py times both). */
+			bool lockstep_enabled()
+			{
+				const char* env = std::getenv("MLPP_KMEANS_LOCKSTEP");
+				return !(env && env[0] == '0');
+			}
+		}
+
 		KMeans::KMeans(unsigned int number_clusters)
 			: labels_on_host_(true)
 			, centroids_initialiser_(std::make_shared<Forgy>())
@@ -85,7 +97,7 @@ namespace ml
 			detail::KmDevice& device = *device_;
 			if (number_initialisations_ == 1) {
 				fit_once(data, device);
-			} else if (!verbose_ && detail::KmSetsDevice::supported(*device.data(), number_clusters_, 2)) {
+			} else if (!verbose_ && lockstep_enabled() && detail::KmSetsDevice::supported(*device.data(), number_clusters_, 2)) {
 				// Best of number_initialisations_ runs by inertia (KMeans.cpp:29-47), the runs advanced in lockstep.
 				return fit_lockstep(data, device);
 			} else {

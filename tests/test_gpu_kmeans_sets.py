@@ -53,10 +53,14 @@ def test_start_sets_equal_the_starts_run_alone(cabi, ctx, n, d, k, n_sets):
         inertia, changed = sets.assign()
         shift = sets.update()
         for s in range(n_sets):
-            assert (inertia[s], changed[s], shift[s]) == alone[s][0][it], (it, s)
+            # labels (hence changed counts, statistics, centroids and their shift) are bit for bit the start's own; a chunk's
+            # inertia partial is summed per warp, so it is exact only when both objects run the same number of warps per CTA
+            # (they do whenever the sets' centroid images leave room for it)
+            assert (changed[s], shift[s]) == alone[s][0][it][1:], (it, s)
+            assert abs(inertia[s] - alone[s][0][it][0]) <= 1e-14 * inertia[s], (it, s)
     inertia, changed = sets.assign()
     for s in range(n_sets):
-        assert inertia[s] == alone[s][1] and changed[s] == alone[s][2], s
+        assert abs(inertia[s] - alone[s][1]) <= 1e-14 * inertia[s] and changed[s] == alone[s][2], s
         assert np.array_equal(sets.get_labels(s), alone[s][3]), s
         assert np.array_equal(sets.get_centroids(s), alone[s][4]), s
     sets.close(); dev.close()

@@ -77,6 +77,40 @@ def test_kmeans_is_bitwise_invariant_in_the_gpu_count():
             assert np.array_equal(a, b), g
 
 
+def _kms_run(n_devices, data, k, starts):
+    from ml_b200 import cabi
+    ctx = cabi.Context(n_devices)
+    d_data = cabi.Data.upload(ctx, data)
+    sets = cabi.Kms(d_data, k, len(starts))
+    for s, c in enumerate(starts):
+        sets.set_centroids(s, c)
+    trace = []
+    for _ in range(3):
+        inertia, changed = sets.assign()
+        trace.append(np.concatenate([inertia, changed.astype(np.float64), sets.update()]))
+    inertia, changed = sets.assign(0b101)
+    out = [np.array(trace), inertia.copy(), changed.copy()] + [sets.get_labels(s) for s in range(len(starts))] + [sets.get_centroids(s) for s in range(len(starts))]
+    sets.close(); d_data.close(); ctx.close()
+    return out
+
+
+@pytest.mark.parametrize("n,d,k", [(30011, 8, 20), (20000, 16, 48)])
+def test_kmeans_start_sets_are_bitwise_invariant_in_the_gpu_count(n, d, k):
+    have = _device_count()
+    if have < 2:
+        pytest.skip("needs at least 2 GPUs")
+    data, _, _ = synthetic_gmm(n, d, 10, seed=64)
+    rng = np.random.default_rng(9)
+    starts = [np.ascontiguousarray(data[rng.choice(n, size=k, replace=False)].T) for _ in range(3)]
+    ref = _kms_run(1, data, k, starts)
+    for g in (2, 4, 8):
+        if g > have:
+            break
+        got = _kms_run(g, data, k, starts)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b), g
+
+
 def _seeding_run(n_devices, data, k, labels):
     """KPP distance passes, the M-step from labels and prediction on a G-GPU context."""
     from ml_b200 import cabi
