@@ -780,7 +780,7 @@ static int launch_em(mlb_em* em, EmKernelFn fn, const EmArgs& a, int g, int grid
     if (a.n_chunks > 0) {
         const bool timed = fn == em->fn_step;
         if (timed) MLB_TRY(em->gpus[g].timer.begin(gpu.stream));
-        fn<<<std::min(grid, a.n_chunks), kEmThreads, em->smem_fused, gpu.stream>>>(a);
+        fn<<<std::min(grid, a.n_chunks), em->DP <= 8 ? kSmallThreads : kEmThreads, em->smem_fused, gpu.stream>>>(a);
         MLB_CUDA(cudaGetLastError());
         if (timed) MLB_TRY(em->gpus[g].timer.end(gpu.stream));
         ++em->launches;
@@ -1472,7 +1472,7 @@ int mlb_em_create(mlb_ctx* ctx, mlb_data* data, int k, mlb_em** out)
             for (EmKernelFn fn : {em->fn_step, em->fn_mstep, em->fn_emit})
                 MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             int per_sm = 0;
-            MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(em->fn_step), kEmThreads, smem));
+            MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(em->fn_step), em->DP <= 8 ? kSmallThreads : kEmThreads, smem));
             MLB_REQUIRE(per_sm >= 1, "mlb_em_create: EM kernel does not fit on an SM");
             eg.grid = per_sm * sms;
         } else if (em->path == 2) {
@@ -1661,7 +1661,7 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
         const size_t smem = DP <= 8 ? em_small_smem_bytes(DP, 8) : em_smem_bytes(DP, 8);
         MLB_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         int per_sm = 0, sms = 0;
-        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), kEmThreads, smem));
+        MLB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), em->DP <= 8 ? kSmallThreads : kEmThreads, smem));
         MLB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, gpu.device));
         MLB_REQUIRE(per_sm >= 1, "mlb_em_sample_covariance: kernel does not fit on an SM");
         EmArgs a = base_args(em, g);
@@ -1669,7 +1669,7 @@ int mlb_em_sample_covariance(mlb_em* em, double* cov_out)
         a.k = 1;
         MLB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned), gpu.stream));
         if (a.n_chunks > 0) {
-            fn<<<std::min(per_sm * sms, a.n_chunks), kEmThreads, smem, gpu.stream>>>(a);
+            fn<<<std::min(per_sm * sms, a.n_chunks), em->DP <= 8 ? kSmallThreads : kEmThreads, smem, gpu.stream>>>(a);
             MLB_CUDA(cudaGetLastError());
             ++em->launches;
         }

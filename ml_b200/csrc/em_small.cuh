@@ -14,6 +14,13 @@
 #pragma once
 
 constexpr int kSmallSub = 16;   // points per warp sub-tile
+// Warps per CTA.  Every warp is self-contained (own sub-tiles, own feature table, own accumulators), so the number is free;
+// what it sets is how many warps share the SM's registers: 4 warps x 4 CTAs at 128 registers (round 1), or 6 x 3 at 112.
+#ifndef MLB_EM_SMALL_NW
+#define MLB_EM_SMALL_NW 4
+#endif
+constexpr int kSmallWarps = MLB_EM_SMALL_NW;
+constexpr int kSmallThreads = kSmallWarps * 32;
 #ifndef MLB_EM_SMALL_MINB
 #define MLB_EM_SMALL_MINB 4
 #endif
@@ -31,11 +38,15 @@ __host__ __device__ constexpr int em_small_nm(int DP) { return (((DP / 4) % 2 ==
 
 constexpr size_t em_small_smem_bytes(int DP, int KP)
 {
-    return sizeof(double) * (em_theta_len(DP, KP) + 4 * kSmallSub * (em_small_nm(DP) * 8 + 4) + 4 * kSmallSub * (KP + 4) + 8 + DP + kExpTableSize);
+    return sizeof(double) * (em_theta_len(DP, KP) + kSmallWarps * kSmallSub * (em_small_nm(DP) * 8 + 4) + kSmallWarps * kSmallSub * (KP + 4) + 8 + DP + kExpTableSize);
 }
 
 template <int DP, int KP, int MODE>
-__global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) * (KP / 8) <= 6) ? MLB_EM_SMALL_MINB_K8 : (em_small_nm(DP) * (KP / 8) <= 12) ? MLB_EM_SMALL_MINB : 3)) em_small_kernel(const EmArgs p)
+#ifdef MLB_EM_SMALL_MAXNREG
+__global__ void __maxnreg__(MLB_EM_SMALL_MAXNREG) em_small_kernel(const EmArgs p)
+#else
+__global__ void __launch_bounds__(kSmallThreads, MODE == 2 ? (kSmallWarps > 4 ? 3 : 4) : ((em_small_nm(DP) * (KP / 8) <= 6) ? MLB_EM_SMALL_MINB_K8 : (em_small_nm(DP) * (KP / 8) <= 12) ? MLB_EM_SMALL_MINB : 3)) em_small_kernel(const EmArgs p)
+#endif
 {
     constexpr int NT = KP / 8, DQ = DP / 4, NE = em_ne(DP), NM = em_small_nm(DP);
     constexpr int RS = KP + 4, PS = NM * 8 + 4;
@@ -48,9 +59,9 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
     extern __shared__ __align__(16) double sm[];
     double* thE = sm;
     double* cE = thE + NE * NT * 32;
-    double* Phi = cE + KP;                        // [4][16][PS] feature rows (products | z | count); reused as the chunk-end reduction buffer
-    double* Rw = Phi + 4 * kSmallSub * PS;        // [4][16][RS]
-    double* wl = Rw + 4 * kSmallSub * RS;
+    double* Phi = cE + KP;                        // [warps][16][PS] feature rows (products | z | count); reused as the chunk-end reduction buffer
+    double* Rw = Phi + kSmallWarps * kSmallSub * PS;        // [warps][16][RS]
+    double* wl = Rw + kSmallWarps * kSmallSub * RS;
     double* sh = wl + 8;
     double* etab = sh + DP;
     __shared__ int s_next;
@@ -59,9 +70,9 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
     const int d = p.d;
 
     if (MODE != 1)
-        for (int i = tid; i < em_theta_len(DP, KP); i += kEmThreads) sm[i] = p.theta[i];
-    for (int i = tid; i < 4 * kSmallSub * PS; i += kEmThreads) Phi[i] = 0.0;
-    for (int i = tid; i < 4 * kSmallSub * RS; i += kEmThreads) Rw[i] = 0.0;
+        for (int i = tid; i < em_theta_len(DP, KP); i += kSmallThreads) sm[i] = p.theta[i];
+    for (int i = tid; i < kSmallWarps * kSmallSub * PS; i += kSmallThreads) Phi[i] = 0.0;
+    for (int i = tid; i < kSmallWarps * kSmallSub * RS; i += kSmallThreads) Rw[i] = 0.0;
     if (tid < DP) sh[tid] = tid < d ? p.shift[tid] : 0.0;
     load_exp_table(etab);
 
@@ -115,14 +126,14 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
         double ll_acc = 0.0, ll_prod = 1.0;
         int nlogged = 0;
 
-        // warp w takes the sub-tiles w, w + 4, w + 8, ... of the chunk
+        // warp w takes the sub-tiles w, w + warps, w + 2 warps, ... of the chunk
         if (warp < nsubs) load_sub(p_begin + static_cast<long long>(warp) * kSmallSub, static_cast<int>(min64(kSmallSub, p_end - p_begin - static_cast<long long>(warp) * kSmallSub)));
-        for (int t = warp; t < nsubs; t += 4) {
+        for (int t = warp; t < nsubs; t += kSmallWarps) {
             const long long tile0 = p_begin + static_cast<long long>(t) * kSmallSub;
             const int nvalid = static_cast<int>(min64(kSmallSub, p_end - tile0));
             __syncwarp();
             store_sub(nvalid);
-            if (t + 4 < nsubs) load_sub(tile0 + 4 * kSmallSub, static_cast<int>(min64(kSmallSub, p_end - tile0 - 4 * kSmallSub)));
+            if (t + kSmallWarps < nsubs) load_sub(tile0 + kSmallWarps * kSmallSub, static_cast<int>(min64(kSmallSub, p_end - tile0 - kSmallWarps * kSmallSub)));
             __syncwarp();
 
             const double* z0 = F + g * PS + LIN;
@@ -290,9 +301,9 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
 
         if (MODE != 2) {
             ll_acc += log(ll_prod);
-            // ---------------- chunk partial: the four warps' statistics added in the fixed order ((w0 + w1) + w2) + w3
+            // ---------------- chunk partial: the warps' statistics added in the fixed order ((w0 + w1) + w2) + w3 ...
             double* red = Phi;   // NM * 8 * KP doubles; every warp is past its last read of the feature table
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < kSmallWarps; ++w) {
                 __syncthreads();
                 if (warp == w) {
 #pragma unroll
@@ -315,12 +326,16 @@ __global__ void __launch_bounds__(kEmThreads, MODE == 2 ? 4 : ((em_small_nm(DP) 
             if (lane == 0) wl[warp] = ll_acc;
             __syncthreads();
             double* out = p.partials + static_cast<long long>(chunk) * SV;
-            for (int i = tid; i < NM * 8 * KP; i += kEmThreads) out[i] = red[i];
-            if (tid == 0) out[NM * 8 * KP] = (wl[0] + wl[1]) + (wl[2] + wl[3]);
+            for (int i = tid; i < NM * 8 * KP; i += kSmallThreads) out[i] = red[i];
+            if (tid == 0) {
+                double ll = (wl[0] + wl[1]) + (wl[2] + wl[3]);
+                for (int w = 4; w < kSmallWarps; ++w) ll += wl[w];
+                out[NM * 8 * KP] = ll;
+            }
             if (tid >= 1 && tid < 8) out[NM * 8 * KP + tid] = 0.0;
             __syncthreads();
             // the feature table must be clean again (dead slots and padding rows are read as zeros by the M-step)
-            for (int i = tid; i < NM * 8 * KP && i < 4 * kSmallSub * PS; i += kEmThreads) Phi[i] = 0.0;
+            for (int i = tid; i < NM * 8 * KP && i < kSmallWarps * kSmallSub * PS; i += kSmallThreads) Phi[i] = 0.0;
         }
     }
 }
