@@ -92,3 +92,22 @@ def test_pinned_host_memory_takes_the_direct_path(cabi, ctx):
     cabi.check(cabi.lib().mlb_data_download(dev._h, 0, n, ctypes.c_void_p(out.data_ptr())))
     assert np.array_equal(out.numpy(), view)
     dev.close()
+
+
+@pytest.mark.parametrize("n,d,offset", [(3_000_000, 8, 0), (2_500_001, 16, 3), (1_100_000, 5, 1)])
+def test_upload_by_registration_round_trip(cabi, ctx, monkeypatch, n, d, offset):
+    """The opt-in upload path MLB200_UPLOAD=register (the caller's pages pinned piece by piece, read by the DMA engine
+    directly; context.cu registered_h2d): the points come back bit for bit, also from a buffer that does not start on
+    a page boundary, and the memory is an ordinary pageable array again afterwards (a second upload pins it again)."""
+    rng = np.random.default_rng(n)
+    backing = rng.normal(size=n * d + 8)
+    points = backing[offset: offset + n * d].reshape(n, d)       # 8 * offset bytes into the allocation
+    monkeypatch.setenv("MLB200_UPLOAD", "register")
+    for _ in range(2):
+        dev = cabi.Data.upload(ctx, points)
+        assert np.array_equal(dev.download(0, n), points)
+        dev.close()
+    monkeypatch.setenv("MLB200_UPLOAD", "staged")
+    dev = cabi.Data.upload(ctx, points)
+    assert np.array_equal(dev.download(n - 1000, 1000), points[-1000:])
+    dev.close()
