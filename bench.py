@@ -678,6 +678,13 @@ def main():
             if os.path.exists(prof):
                 entry = json.load(open(prof)).get(args.workload)
                 if entry is not None:
+                    if "captured_points" in entry:
+                        # ncu capture of one launch at `captured_points` points: the kernels stream the points once and
+                        # write per-chunk partials, both linear in N, so the capture is scaled to this launch's points
+                        scale = n_per_gpu / entry["captured_points"]
+                        entry = {"bytes_per_launch": (entry["dram_read"] + entry["dram_write"]) * scale, "dram_read": entry["dram_read"] * scale,
+                                 "dram_write": entry["dram_write"] * scale, "algorithmic_bytes": entry["algorithmic_bytes_per_point"] * n_per_gpu,
+                                 "source": entry["source"] + f"; scaled by {scale:.3f} to the {n_per_gpu} points of this launch"}
                     line["roofline"]["traffic"] = entry
                     break
         if per_rank is not None:
