@@ -329,6 +329,11 @@ def run_reference(args):
     }
     if ref_build:
         line["reference_build"] = ref_build
+    # for the record: what all the host's cores give when the data is sharded by hand over independent single-threaded
+    # fits (the reference has no threads of its own; `value` above is the reference as it runs)
+    all_cores = cpu_all_cores(max(4 * k, n_cpu // 4), d, k, 3, 1, kind)
+    if all_cores:
+        line["cpu_baseline"]["all_cores"] = all_cores
     print(json.dumps(line), flush=True)
 
 
