@@ -113,6 +113,20 @@ def test_kmeans_on_the_reference_test_data(init, inits):
         assert label == b.query_labels[i] and close(sq, b.query_distances[i], False)
 
 
+@pytest.mark.parametrize("inits,max_steps", [(3, 2), (5, 3), (4, 100), (6, 100)])
+def test_kmeans_multi_start_with_and_without_convergence(inits, max_steps):
+    """KMeans.cpp:29-47 when some or all starts run out of steps: the best CONVERGED start wins; when none converged the
+    object is left in the last start's state (labels of its last assignment, centroids of its last update).  The device
+    path's lockstep multi-start (ml_b200/host/src/KMeans.cpp, fit_lockstep) is tested against the port on exactly these
+    cases (tests/test_gpu_kmeans_sets.py), so the port is pinned to the reference's own code on them here."""
+    data, _ = oracle.testdata_mouse(4000)
+    kw = dict(seed=77, init=oracle.KPP, absolute_tolerance=1e-14, number_initialisations=inits, maximum_steps=max_steps)
+    a = oracle.kmeans_fit(data, 3, **kw)
+    b = oracle.kmeans_fit(data, 3, impl="reference", **kw)
+    b.iterations = a.iterations   # not observable from outside for a multi-start fit
+    same_kmeans(a, b)
+
+
 @pytest.mark.parametrize("n,d,k,seed", [(4000, 2, 3, 1), (3000, 8, 16, 2), (2000, 32, 40, 3), (1000, 1, 4, 4)])
 def test_kmeans_on_synthetic_mixtures(n, d, k, seed):
     data, _, _ = synthetic_gmm(n, d, min(k, 12), seed=seed, spread=5.0)
